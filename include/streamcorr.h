@@ -1,0 +1,115 @@
+/* streamcorr.h -- C ABI of libstreamcorr.so, the B200 (sm_100a) implementation of StreamFlow's
+ * per-iteration correlation hot path.
+ *
+ * The reference (littlespray/StreamFlow) has no FFI of its own: the boundary of this path is its Python
+ * operator API.  Each entry point below replaces the body of one reference operator; the Python mirror
+ * in streamflow_b200/{corr,gma}.py binds them with ctypes:
+ *
+ *   sf_corr_build           <- CorrBlock.__init__ + CorrBlock.corr     core/corr.py:7-21, 46-54
+ *   sf_corr_lookup[_group]  <- CorrBlock.__call__ + bilinear_sampler   core/corr.py:23-44, core/utils/utils.py:65-79
+ *   sf_gma_attention        <- gma.Attention.forward                   core/gma.py:53-65
+ *   sf_gma_aggregate        <- gma.Aggregate.forward                   core/gma.py:91-104
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; the library never
+ *     allocates or frees caller-visible memory (workspaces are sized by the *_workspace_bytes queries);
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns without synchronising,
+ *     so all calls are CUDA-graph capturable;
+ *   - return value 0 = success, negative = error; sf_last_error() returns a thread-local message;
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry point fails.
+ */
+#ifndef STREAMCORR_H_
+#define STREAMCORR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SF_API __attribute__((visibility("default")))
+#else
+#define SF_API
+#endif
+
+#define SF_VERSION 100          /* major*100 + minor */
+#define SF_NUM_LEVELS 4         /* corr_levels fixed by the model: core/models/streamflow.py:38 */
+#define SF_RADIUS 4             /* corr_radius fixed by the model: core/models/streamflow.py:39 */
+#define SF_MAX_GROUPS 8         /* CorrBlocks batched into one lookup launch */
+
+/* error codes */
+#define SF_OK 0
+#define SF_ERR_INVALID (-1)     /* bad argument (shape, alignment, unsupported specialisation) */
+#define SF_ERR_CUDA (-2)        /* CUDA runtime / driver error, message has the detail */
+#define SF_ERR_NODEVICE (-3)    /* no sm_100 device: the library has no fallback path */
+#define SF_ERR_WORKSPACE (-4)   /* workspace too small */
+
+/* precision of the correlation GEMM (stated per north_star: fp32 accumulate in every mode) */
+#define SF_PREC_F16 0           /* operands rounded to fp16 after a per-tensor power-of-two scale; EXACT
+                                   products when the feature maps are fp16-representable (the model's
+                                   mixed-precision path, core/models/streamflow.py:107); 2^-11 operand
+                                   rounding otherwise (same mantissa as TF32)                                */
+#define SF_PREC_F16X2 1         /* hi/lo split fp16 operands, 3 tensor-core products: ~2^-21, fp32-faithful  */
+#define SF_PREC_FP32_SIMT 2     /* plain fp32 FFMA tiles + hierarchical pooling: the reference's arithmetic  */
+
+/* dtype codes for tensors whose element type may vary */
+#define SF_DT_F32 0
+#define SF_DT_F16 1
+#define SF_DT_BF16 2
+
+SF_API int sf_version(void);
+SF_API const char* sf_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x), SF_ERR_NODEVICE otherwise */
+SF_API int sf_device_ok(void);
+
+/* ---- correlation pyramid -------------------------------------------------------------------------
+ * Level l of the pyramid is a dense matrix [B*N, h_l * pitch_l] fp32 (N = h*w): row b*N + y*w + x is the
+ * h_l x w_l correlation image of query (b,y,x), rows padded to pitch_l = round_up(w_l, 4) floats with
+ * zeros.  h_l = h >> l, w_l = w >> l (avg_pool2d(2,2) floor mode, core/corr.py:19-21).                */
+SF_API void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* pitch_l);
+SF_API int64_t sf_corr_workspace_bytes(int64_t B, int64_t D, int64_t h, int64_t w, int precision);
+
+/* fmap1/fmap2: [B, D, h, w] fp32 with arbitrary element strides {sB, sD, sh, sw} (the model passes
+ * channels-last views).  levels[l]: output buffers as described above, 16-byte aligned.               */
+SF_API int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, int64_t h, int64_t w,
+                  const int64_t f1_strides[4], const int64_t f2_strides[4], float* const levels[SF_NUM_LEVELS],
+                  void* workspace, int64_t workspace_bytes, int precision, void* stream);
+
+/* coords [B, 2, h, w] fp32 contiguous (channel 0 = x, 1 = y) -> out [B, 4*81, h, w] fp32 contiguous;
+ * channel l*81 + i*9 + j samples level l bilinearly (zeros outside, align_corners) at
+ * (x, y) = (cx / 2^l + i - 4, cy / 2^l + j - 4).                                                       */
+SF_API int sf_corr_lookup(const float* const levels[SF_NUM_LEVELS], const float* coords, float* out, int64_t B,
+                   int64_t h, int64_t w, int radius, int num_levels, void* stream);
+
+/* G CorrBlocks of identical shape in ONE launch (the T-1 frame pairs of a clip, streamflow.py:132).
+ * levels: G*4 pointers (group-major); coords, out: G pointers.  out[g] may point into one
+ * [G*B, 324, h, w] tensor so the stack + rearrange of the caller disappears.
+ * out_dtype: SF_DT_F32 (reference layout) or SF_DT_F16 (for the autocast consumer).                    */
+SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* const* coords, void* const* out,
+                         int out_dtype, int64_t B, int64_t h, int64_t w, int radius, int num_levels, void* stream);
+
+/* ---- GMA ------------------------------------------------------------------------------------------
+ * heads = 1, dim = dim_head = d (128 in the shipped model, core/models/streamflow.py:49).
+ * sf_gma_attention computes, once per clip, E[p,i,j] = fp16(2^12 * exp(s_ij - max_j s_ij)) with
+ * s = (d^-1/2 * q) . k, q,k = W_qk . fmap, and rinv[p,i] = 1 / (2^12 ... sum_j E[p,i,j]) so that
+ * softmax = E * rinv.  E: [P, N, Npad] fp16, Npad = round_up(N, 64).
+ * sf_gma_aggregate computes out = fmap + gamma * ((E * rinv) . (W_v . fmap)^T) every iteration.        */
+SF_API int64_t sf_gma_npad(int64_t N);
+SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);
+
+/* fmap: [P, C, N] (NCHW flattened, contiguous) of dtype fmap_dtype; w_qk: [2*d, C] fp32 contiguous.  */
+SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N,
+                     int64_t d, float scale, void* E, float* rinv, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+
+/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] fp32; gamma: device pointer to 1 float;
+ * out: [P, C, N] fp32 (requires C == d: the reference's `project` is None, core/gma.py:86-89).         */
+SF_API int sf_gma_aggregate(const void* E, const float* rinv, const void* fmap, int fmap_dtype, const float* w_v,
+                     const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STREAMCORR_H_ */

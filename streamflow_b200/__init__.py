@@ -1,0 +1,11 @@
+"""streamflow_b200 -- B200 (sm_100a) implementation of StreamFlow's correlation / GMA hot path.
+
+Public surface mirrors the reference operators (``core/corr.py``, ``core/gma.py``):
+``CorrBlock``, ``Attention``, ``Aggregate`` (+ ``CorrGroup`` for pair-batched lookups and
+``install()`` to make ``from corr import CorrBlock`` / ``from gma import Attention, Aggregate``
+resolve to these classes so the unchanged StreamFlow model code runs on them).
+"""
+from ._lib import StreamCorrError, lib  # noqa: F401
+from .corr import CorrBlock, CorrGroup, coords_grid  # noqa: F401
+
+__all__ = ["CorrBlock", "CorrGroup", "coords_grid", "StreamCorrError", "lib"]

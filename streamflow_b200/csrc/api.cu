@@ -1,0 +1,316 @@
+// C ABI of libstreamcorr.so (declared in include/streamcorr.h): argument validation, workspace carving,
+// TMA tensor-map construction and kernel launches.  No torch types, no allocation, no host synchronisation.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sf_internal.h"
+
+namespace sf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+LevelGeom make_level_geom(int64_t h, int64_t w) {
+    LevelGeom g;
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        g.h[l] = static_cast<int>(h >> l);
+        g.w[l] = static_cast<int>(w >> l);
+        g.pitch[l] = (g.w[l] + 3) & ~3;
+        g.img[l] = static_cast<long long>(g.h[l]) * g.pitch[l];
+    }
+    return g;
+}
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceInfo {
+    int ok = -1;      // -1 unknown, 0 unusable, 1 usable
+    int sms = 0;
+    int dev = -1;
+};
+
+int query_device(DeviceInfo* out) {
+    static thread_local DeviceInfo cache;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libstreamcorr has no CPU fallback");
+        return SF_ERR_NODEVICE;
+    }
+    if (cache.ok < 0 || cache.dev != dev) {
+        int major = 0, sms = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cannot query CUDA device %d", dev);
+            return SF_ERR_NODEVICE;
+        }
+        cache.dev = dev;
+        cache.sms = sms;
+        cache.ok = (major == 10) ? 1 : 0;
+    }
+    if (cache.ok != 1) {
+        set_error("device %d is not sm_100 (Blackwell B200): kernels are built for sm_100a only, no fallback", dev);
+        return SF_ERR_NODEVICE;
+    }
+    *out = cache;
+    return SF_OK;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// rank-3 tiled map: dims / box innermost first; strides (bytes) for dims 1 and 2.
+int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return SF_ERR_CUDA;
+    }
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {stride1, stride2};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)", what,
+                  static_cast<int>(r), (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                  (unsigned long long)stride1, (unsigned long long)stride2);
+        return SF_ERR_CUDA;
+    }
+    return SF_OK;
+}
+
+int check_corr_shape(int64_t B, int64_t D, int64_t h, int64_t w) {
+    SF_REQUIRE(B >= 1 && D >= 1 && h >= 1 && w >= 1, "corr: non-positive shape B=%lld D=%lld h=%lld w=%lld",
+               (long long)B, (long long)D, (long long)h, (long long)w);
+    // the reference divides by (h_l - 1) and (w_l - 1) when normalising (core/utils/utils.py:69-70)
+    SF_REQUIRE((h >> (SF_NUM_LEVELS - 1)) >= 2 && (w >> (SF_NUM_LEVELS - 1)) >= 2,
+               "corr: %lldx%lld is too small for a %d-level pyramid (coarsest level must be at least 2x2)",
+               (long long)h, (long long)w, SF_NUM_LEVELS);
+    SF_REQUIRE(B * h * w < (1ll << 31) && h * w * 2 < (1ll << 31), "corr: shape too large");
+    return SF_OK;
+}
+
+struct CorrWs {
+    int64_t amax_off, a_off, b_off[SF_NUM_LEVELS], total;
+    int Kp;
+};
+
+CorrWs corr_ws_layout(int64_t B, int64_t D, int64_t h, int64_t w, int precision) {
+    CorrWs ws{};
+    const LevelGeom g = make_level_geom(h, w);
+    const int64_t N = h * w;
+    if (precision == SF_PREC_FP32_SIMT) {
+        ws.a_off = 0;
+        ws.b_off[0] = align_up(B * D * N * 4, 256);
+        ws.total = ws.b_off[0] + align_up(B * D * N * 4, 256);
+        ws.Kp = static_cast<int>(D);
+        return ws;
+    }
+    ws.Kp = static_cast<int>(precision == SF_PREC_F16X2 ? 3 * D : D);
+    int64_t off = 0;
+    ws.amax_off = off;
+    off += 256;
+    ws.a_off = off;
+    off += align_up(B * N * ws.Kp * 2, 1024);
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        ws.b_off[l] = off;
+        off += align_up(B * g.img[l] * ws.Kp * 2, 1024);
+    }
+    ws.total = off;
+    return ws;
+}
+
+}  // namespace
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" {
+
+int sf_version(void) { return SF_VERSION; }
+
+const char* sf_last_error(void) { return g_err; }
+
+int sf_device_ok(void) {
+    DeviceInfo di;
+    return query_device(&di);
+}
+
+void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* pitch_l) {
+    const int64_t hl = h >> level, wl = w >> level;
+    if (h_l) *h_l = hl;
+    if (w_l) *w_l = wl;
+    if (pitch_l) *pitch_l = (wl + 3) & ~int64_t(3);
+}
+
+int64_t sf_corr_workspace_bytes(int64_t B, int64_t D, int64_t h, int64_t w, int precision) {
+    if (B < 1 || D < 1 || h < 1 || w < 1) return 0;
+    return corr_ws_layout(B, D, h, w, precision).total;
+}
+
+int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, int64_t h, int64_t w,
+                  const int64_t f1_strides[4], const int64_t f2_strides[4], float* const levels[SF_NUM_LEVELS],
+                  void* workspace, int64_t workspace_bytes, int precision, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    if (int rc = check_corr_shape(B, D, h, w)) return rc;
+    SF_REQUIRE(fmap1 && fmap2 && levels && f1_strides && f2_strides, "corr_build: null pointer argument");
+    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2 || precision == SF_PREC_FP32_SIMT,
+               "corr_build: unknown precision mode %d", precision);
+    for (int l = 0; l < SF_NUM_LEVELS; ++l)
+        SF_REQUIRE(levels[l] && (reinterpret_cast<uintptr_t>(levels[l]) & 15) == 0,
+                   "corr_build: level %d buffer is null or not 16-byte aligned", l);
+    const CorrWs ws = corr_ws_layout(B, D, h, w, precision);
+    if (!workspace || workspace_bytes < ws.total) {
+        set_error("corr_build: workspace of %lld bytes needed, %lld given", (long long)ws.total,
+                  (long long)workspace_bytes);
+        return SF_ERR_WORKSPACE;
+    }
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "corr_build: workspace must be 1024-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const LevelGeom g = make_level_geom(h, w);
+    const int64_t N = h * w;
+
+    if (precision == SF_PREC_FP32_SIMT) {
+        return launch_corr_simt(fmap1, fmap2, B, D, h, w, f1_strides, f2_strides, levels,
+                                reinterpret_cast<float*>(wsb + ws.a_off), reinterpret_cast<float*>(wsb + ws.b_off[0]),
+                                s);
+    }
+
+    SF_REQUIRE(D % 8 == 0, "corr_build: tensor-core modes need D %% 8 == 0 (got %lld); use SF_PREC_FP32_SIMT",
+               (long long)D);
+    unsigned* amax = reinterpret_cast<unsigned*>(wsb + ws.amax_off);
+    if (int rc = launch_absmax2(fmap1, fmap2, B, D, h, w, f1_strides, f2_strides, amax, s)) return rc;
+
+    PackParams pp{};
+    pp.nseg = 1 + SF_NUM_LEVELS;
+    pp.D = static_cast<int>(D);
+    pp.split = (precision == SF_PREC_F16X2);
+    pp.amax_bits = amax;
+    int tile = 0;
+    {
+        PackSeg& a = pp.seg[0];
+        a.src = fmap1;
+        a.sb = f1_strides[0]; a.sk = f1_strides[1]; a.sy = f1_strides[2]; a.sx = f1_strides[3];
+        a.dst = reinterpret_cast<__half*>(wsb + ws.a_off);
+        a.hl = (int)h; a.wl = (int)w; a.pitch = (int)w; a.level = 0;
+        a.rows = (int)N; a.tile0 = tile; a.amax_slot = 0; a.is_b = 0;
+        tile += (a.rows + 31) / 32;
+    }
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        PackSeg& b = pp.seg[1 + l];
+        b.src = fmap2;
+        b.sb = f2_strides[0]; b.sk = f2_strides[1]; b.sy = f2_strides[2]; b.sx = f2_strides[3];
+        b.dst = reinterpret_cast<__half*>(wsb + ws.b_off[l]);
+        b.hl = g.h[l]; b.wl = g.w[l]; b.pitch = g.pitch[l]; b.level = l;
+        b.rows = (int)g.img[l]; b.tile0 = tile; b.amax_slot = 1; b.is_b = 1;
+        tile += (b.rows + 31) / 32;
+    }
+    if (int rc = launch_corr_pack(pp, tile, B, s)) return rc;
+
+    CorrGemmParams gp{};
+    gp.B = (int)B; gp.N = (int)N; gp.Kp = ws.Kp;
+    gp.m_tiles = (int)((N + 127) / 128);
+    gp.n_tiles_total = 0;
+    int n_cols[SF_NUM_LEVELS];
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        gp.n_tiles[l] = (int)((g.img[l] + 255) / 256);
+        gp.n_tiles_total += gp.n_tiles[l];
+        n_cols[l] = (int)g.img[l];
+    }
+    gp.amax_bits = amax;
+    gp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
+
+    CUtensorMap tm_a, tm_b[SF_NUM_LEVELS], tm_out[SF_NUM_LEVELS];
+    const uint64_t kp = static_cast<uint64_t>(ws.Kp);
+    if (int rc = make_tmap3(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.a_off, kp, N, B, kp * 2, N * kp * 2, 64,
+                            128, "A"))
+        return rc;
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        const uint64_t rows = static_cast<uint64_t>(g.img[l]);
+        if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
+                                rows * kp * 2, 64, 256, "B"))
+            return rc;
+        if (int rc = make_tmap3(&tm_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, levels[l], rows, N, B, rows * 4,
+                                N * rows * 4, 32, 32, "level"))
+            return rc;
+    }
+    return launch_corr_gemm(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s);
+}
+
+static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,
+                         int out_dtype, int64_t B, int64_t h, int64_t w, int radius, int num_levels, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    if (int rc = check_corr_shape(B, 1, h, w)) return rc;
+    SF_REQUIRE(radius == SF_RADIUS && num_levels == SF_NUM_LEVELS,
+               "corr_lookup: specialised for radius=%d, num_levels=%d (got %d, %d); no generic fallback", SF_RADIUS,
+               SF_NUM_LEVELS, radius, num_levels);
+    SF_REQUIRE(G >= 1 && G <= SF_MAX_GROUPS, "corr_lookup: group count %d outside [1, %d]", G, SF_MAX_GROUPS);
+    SF_REQUIRE(out_dtype == SF_DT_F32 || out_dtype == SF_DT_F16, "corr_lookup: unsupported output dtype %d", out_dtype);
+    SF_REQUIRE(levels && coords && out, "corr_lookup: null pointer argument");
+    const LevelGeom g = make_level_geom(h, w);
+    LookupParams p{};
+    for (int gi = 0; gi < G; ++gi) {
+        for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+            const float* lp = levels[gi * SF_NUM_LEVELS + l];
+            SF_REQUIRE(lp && (reinterpret_cast<uintptr_t>(lp) & 15) == 0,
+                       "corr_lookup: level buffer (group %d, level %d) null or not 16-byte aligned", gi, l);
+            p.lvl[gi][l] = lp;
+        }
+        SF_REQUIRE(coords[gi] && out[gi], "corr_lookup: null coords/out for group %d", gi);
+        p.coords[gi] = coords[gi];
+        p.out[gi] = out[gi];
+    }
+    for (int l = 0; l < SF_NUM_LEVELS; ++l) {
+        p.hl[l] = g.h[l]; p.wl[l] = g.w[l]; p.pitch[l] = g.pitch[l]; p.img[l] = g.img[l];
+    }
+    p.N = (int)(h * w);
+    p.BN = B * h * w;
+    p.out_f16 = (out_dtype == SF_DT_F16);
+    return launch_corr_lookup(p, G, static_cast<cudaStream_t>(stream));
+}
+
+int sf_corr_lookup(const float* const levels[SF_NUM_LEVELS], const float* coords, float* out, int64_t B, int64_t h,
+                   int64_t w, int radius, int num_levels, void* stream) {
+    void* o = out;
+    return lookup_common(1, levels, &coords, &o, SF_DT_F32, B, h, w, radius, num_levels, stream);
+}
+
+int sf_corr_lookup_group(int G, const float* const* levels, const float* const* coords, void* const* out,
+                         int out_dtype, int64_t B, int64_t h, int64_t w, int radius, int num_levels, void* stream) {
+    return lookup_common(G, levels, coords, out, out_dtype, B, h, w, radius, num_levels, stream);
+}
+
+}  // extern "C"

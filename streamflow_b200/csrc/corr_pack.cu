@@ -1,0 +1,173 @@
+// Operand preparation for the correlation GEMM (part of CorrBlock.__init__, core/corr.py:7-21).
+//
+//  absmax2_kernel   per-tensor |max| of fmap1 / fmap2 (device-side, no host sync) -> power-of-two scale.
+//  corr_pack_kernel reads the fp32 feature maps through their ORIGINAL strides (the model hands over
+//                   channels-last views, core/models/streamflow.py:107,110) and writes K-major fp16 operand
+//                   matrices the TMA can tile:  A = fmap1 as [B, N, Kp];  B_l = avg-pooled fmap2 at level l
+//                   as [B, h_l*pitch_l, Kp] (rows at pad columns are zero).  Pooling the operand instead of
+//                   the volume uses linearity: avg_pool(f1^T f2) == f1^T avg_pool(f2) (core/corr.py:19-21).
+//                   With split != 0 each value is stored as hi/lo fp16 parts concatenated along K so that one
+//                   GEMM over Kp = 3*D accumulates  hi*hi + hi*lo + lo*hi  (fp32-faithful mode).
+#include "sf_internal.h"
+
+namespace sf {
+
+namespace {
+
+struct Strided4 {
+    const float* p;
+    long long sb, sk, sy, sx;
+};
+
+__global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, long long per_batch,
+                               long long total, unsigned* out_bits) {
+    const Strided4 t = blockIdx.y == 0 ? t0 : t1;
+    float m = 0.f;
+    const int hw = h * w;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long b = i / per_batch;
+        const int rem = static_cast<int>(i - b * per_batch);
+        // enumerate in an order that is contiguous for both NCHW (sx == 1) and channels-last (sk == 1)
+        int k, y, x;
+        if (t.sk == 1) {
+            k = rem % D;
+            const int n = rem / D;
+            y = n / w;
+            x = n - y * w;
+        } else {
+            k = rem / hw;
+            const int n = rem - k * hw;
+            y = n / w;
+            x = n - y * w;
+        }
+        m = fmaxf(m, fabsf(__ldg(t.p + b * t.sb + k * t.sk + y * t.sy + x * t.sx)));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float src_at(const PackSeg& s, long long boff, int k, int y, int x) {
+    return __ldg(s.src + boff + k * s.sk + y * s.sy + x * s.sx);
+}
+
+// 2x2 average pooling applied `level` times (floor mode): same nesting as the reference's repeated avg_pool2d.
+__device__ float pooled_at(const PackSeg& s, long long boff, int k, int v, int u) {
+    if (s.level == 0) return src_at(s, boff, k, v, u);
+    if (s.level == 1) {
+        const int y = 2 * v, x = 2 * u;
+        return 0.25f * ((src_at(s, boff, k, y, x) + src_at(s, boff, k, y, x + 1)) +
+                        (src_at(s, boff, k, y + 1, x) + src_at(s, boff, k, y + 1, x + 1)));
+    }
+    const int half = 1 << (s.level - 1);     // side of the level-(l-1) block in source pixels
+    float quad[4];
+#pragma unroll
+    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < 2; ++qx) {
+            // value of the level-(l-1) cell (2v+qy, 2u+qx)
+            const int y0 = (2 * v + qy) * half, x0 = (2 * u + qx) * half;
+            float acc;
+            if (s.level == 2) {
+                acc = 0.25f * ((src_at(s, boff, k, y0, x0) + src_at(s, boff, k, y0, x0 + 1)) +
+                               (src_at(s, boff, k, y0 + 1, x0) + src_at(s, boff, k, y0 + 1, x0 + 1)));
+            } else {   // level 3: cell is a 4x4 source block = 2x2 of 2x2 averages
+                float sub[4];
+#pragma unroll
+                for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) {
+                        const int yy = y0 + 2 * sy, xx = x0 + 2 * sx;
+                        sub[sy * 2 + sx] =
+                            0.25f * ((src_at(s, boff, k, yy, xx) + src_at(s, boff, k, yy, xx + 1)) +
+                                     (src_at(s, boff, k, yy + 1, xx) + src_at(s, boff, k, yy + 1, xx + 1)));
+                    }
+                acc = 0.25f * ((sub[0] + sub[1]) + (sub[2] + sub[3]));
+            }
+            quad[qy * 2 + qx] = acc;
+        }
+    return 0.25f * ((quad[0] + quad[1]) + (quad[2] + quad[3]));
+}
+
+// CTA = 32 rows x 64 channels of one segment / batch element.  blockDim = (32, 8).
+__global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ PackParams p) {
+    __shared__ float tile[64][33];
+
+    int si = 0;
+#pragma unroll
+    for (int i = 1; i < 1 + SF_NUM_LEVELS; ++i)
+        if (i < p.nseg && static_cast<int>(blockIdx.x) >= p.seg[i].tile0) si = i;
+    const PackSeg& s = p.seg[si];
+    const int row0 = (static_cast<int>(blockIdx.x) - s.tile0) * 32;
+    const int k0 = blockIdx.y * 64;
+    const int b = blockIdx.z;
+    const long long boff = b * s.sb;
+    const float scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[s.amax_slot])));
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const bool kfast = (s.sk == 1);
+
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        int kk, rr;
+        if (kfast) {
+            kk = tx + 32 * (it & 1);
+            rr = ty + 8 * (it >> 1);
+        } else {
+            rr = tx;
+            kk = ty + 8 * it;
+        }
+        const int m = row0 + rr;
+        float val = 0.f;
+        if (m < s.rows && k0 + kk < p.D) {
+            const int v = m / s.pitch, u = m - v * s.pitch;
+            if (u < s.wl) val = pooled_at(s, boff, k0 + kk, v, u) * scale;
+        }
+        tile[kk][rr] = val;
+    }
+    __syncthreads();
+
+    const int Kp = p.split ? 3 * p.D : p.D;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int rr = ty + 8 * it;
+        const int m = row0 + rr;
+        const int kk = 2 * tx;
+        if (m >= s.rows || k0 + kk >= p.D) continue;
+        const float v0 = tile[kk][rr], v1 = tile[kk + 1][rr];
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        __half* drow = s.dst + (static_cast<long long>(b) * s.rows + m) * Kp + k0 + kk;
+        *reinterpret_cast<__half2*>(drow) = __halves2half2(h0, h1);
+        if (p.split) {
+            const float l0 = (v0 - __half2float(h0)) * 2048.f, l1 = (v1 - __half2float(h1)) * 2048.f;
+            const __half2 lo = __halves2half2(__float2half_rn(l0), __float2half_rn(l1));
+            const __half2 hs = __halves2half2(__float2half_rn(__half2float(h0) * (1.f / 2048.f)),
+                                              __float2half_rn(__half2float(h1) * (1.f / 2048.f)));
+            *reinterpret_cast<__half2*>(drow + p.D) = s.is_b ? lo : hs;
+            *reinterpret_cast<__half2*>(drow + 2 * p.D) = s.is_b ? hs : lo;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
+                   const int64_t s1[4], const int64_t s2[4], unsigned* amax_bits, cudaStream_t s) {
+    SF_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 2 * sizeof(unsigned), s));
+    Strided4 t0{f1, s1[0], s1[1], s1[2], s1[3]}, t1{f2, s2[0], s2[1], s2[2], s2[3]};
+    const long long per_batch = D * h * w, total = B * per_batch;
+    const int blocks = static_cast<int>(std::min<long long>((total + 1023) / 1024, 1184));
+    absmax2_kernel<<<dim3(blocks, 2), 256, 0, s>>>(t0, t1, static_cast<int>(D), static_cast<int>(h),
+                                                   static_cast<int>(w), per_batch, total, amax_bits);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_corr_pack(const PackParams& p, int total_tiles, int64_t B, cudaStream_t s) {
+    dim3 grid(total_tiles, (p.D + 63) / 64, static_cast<unsigned>(B));
+    corr_pack_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+}  // namespace sf

@@ -1,0 +1,143 @@
+// Internal declarations shared by the kernel translation units and the C-ABI layer (api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/streamcorr.h"
+
+namespace sf {
+
+void set_error(const char* fmt, ...);
+
+#define SF_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::sf::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                        \
+            return SF_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define SF_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::sf::set_error(__VA_ARGS__); \
+            return SF_ERR_INVALID;       \
+        }                                \
+    } while (0)
+
+struct LevelGeom {
+    int h[SF_NUM_LEVELS], w[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS];
+    long long img[SF_NUM_LEVELS];   // floats per query image = h_l * pitch_l
+};
+LevelGeom make_level_geom(int64_t h, int64_t w);
+
+// Power-of-two operand scale derived from a tensor's absmax (bits of a non-negative float):
+// amax * 2^e lands in [2^13, 2^14) so fp16 never overflows; e is clamped to [-40, 40].
+__host__ __device__ inline int scale_exponent_from_bits(unsigned bits) {
+    const int biased = static_cast<int>((bits >> 23) & 0xFF);
+    if (bits == 0u || biased == 0 || biased == 0xFF) return 0;   // zero / denormal / inf-nan: no scaling
+    int e = 13 - (biased - 127);
+    return e < -40 ? -40 : (e > 40 ? 40 : e);
+}
+
+// ------------------------------------------------------------------ lookup (corr_lookup.cu)
+struct LookupParams {
+    const float* lvl[SF_MAX_GROUPS][SF_NUM_LEVELS];
+    const float* coords[SF_MAX_GROUPS];
+    void* out[SF_MAX_GROUPS];
+    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS];
+    long long img[SF_NUM_LEVELS];
+    int N;            // h * w
+    long long BN;     // queries per group
+    int out_f16;
+};
+int launch_corr_lookup(const LookupParams& p, int groups, cudaStream_t s);
+
+// ------------------------------------------------------------- operand packing (corr_pack.cu)
+struct PackSeg {
+    const float* src;            // [B, D, h, w] with element strides sb, sk, sy, sx
+    long long sb, sk, sy, sx;
+    __half* dst;                 // [B, rows, Kp] fp16, K contiguous
+    int hl, wl, pitch, level;    // geometry of the (pooled) target grid; row m = v * pitch + u
+    int rows;                    // hl * pitch
+    int tile0;                   // first 32-row tile of this segment in blockIdx.x space
+    int amax_slot;               // which absmax slot scales this tensor
+    int is_b;                    // split layout: A = [hi | hi*2^-11 | lo*2^11], B = [hi | lo*2^11 | hi*2^-11]
+};
+struct PackParams {
+    PackSeg seg[1 + SF_NUM_LEVELS];
+    int nseg;
+    int D;                       // channels
+    int split;                   // 0: Kp = D, 1: Kp = 3*D
+    const unsigned* amax_bits;   // [2]
+};
+int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
+                   const int64_t s1[4], const int64_t s2[4], unsigned* amax_bits, cudaStream_t s);
+int launch_corr_pack(const PackParams& p, int total_tiles, int64_t B, cudaStream_t s);
+
+// --------------------------------------------------------- strict fp32 path (corr_simt.cu)
+int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
+                     const int64_t s1[4], const int64_t s2[4], float* const levels[SF_NUM_LEVELS],
+                     float* ws_a, float* ws_b, cudaStream_t s);
+
+// ----------------------------------------------------- tcgen05 GEMM (corr_gemm_sm100.cu)
+struct CorrGemmParams {
+    int B, N, Kp;                          // batch (pairs), queries per pair, packed K (multiple of 64)
+    int m_tiles;                           // ceil(N / 128)
+    int n_tiles[SF_NUM_LEVELS];            // ceil(rows_l / 256)
+    int n_tiles_total;
+    const unsigned* amax_bits;             // [2] operand scales (device)
+    float inv_sqrt_d;
+};
+int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
+                     const CUtensorMap tm_out[SF_NUM_LEVELS], const int n_cols[SF_NUM_LEVELS], int num_sms,
+                     cudaStream_t s);
+
+// ----------------------------------------------------------------------- GMA (gma_sm100.cu)
+struct GmaProjParams {
+    const void* x;        // [P, C, N]
+    int x_dtype;
+    const float* w;       // [O, C] rows o0 .. o0+O-1 used
+    int P, C, N, O;
+    float scale;          // multiplies the result (q gets d^-1/2)
+    __half* out;          // token-major: [P, Nrows, ldo] (ldo >= O) or channel-major: [P, O, ldn]
+    long long out_batch_stride;
+    int ld;               // row pitch of out in elements
+    int token_major;
+    int split;            // token-major only: also write lo/hi split parts at column offsets O and 2*O
+    int is_b;
+};
+int launch_gma_proj(const GmaProjParams& p, cudaStream_t s);
+
+struct GmaStatsParams {
+    int P, N, Npad, Kp;
+    int m_tiles, n_tiles;       // ceil(N/128), ceil(N/256)
+    int chunks;                 // key-chunks per m-tile (work split)
+    unsigned* rowmax_bits;      // [P, N] ordered-int encoded running max (pass 1 out / pass 2 in)
+    float* rowsum;              // [P, N] sum of stored E (pass 2 out, atomics)
+    __half* E;                  // [P, N, Npad]
+    int pass;
+};
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k, int num_sms,
+                     cudaStream_t s);
+
+struct GmaAggParams {
+    int P, N, Npad, C;          // C == d == 128
+    int m_tiles, k_blocks;      // ceil(N/128), Npad/64
+    float* acc;                 // [P, N, 128] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
+    const float* rowsum;        // [P, N]
+    const void* fmap;           // [P, C, N]
+    int fmap_dtype;
+    const float* gamma;
+    float* out;                 // [P, C, N]
+};
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
+                         cudaStream_t s);
+int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s);
+int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
+
+}  // namespace sf
