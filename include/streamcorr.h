@@ -90,22 +90,27 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
                          int out_dtype, int64_t B, int64_t h, int64_t w, int radius, int num_levels, void* stream);
 
 /* ---- GMA ------------------------------------------------------------------------------------------
- * heads = 1, dim = dim_head = d (128 in the shipped model, core/models/streamflow.py:49).
- * sf_gma_attention computes, once per clip, E[p,i,j] = fp16(2^12 * exp(s_ij - max_j s_ij)) with
- * s = (d^-1/2 * q) . k, q,k = W_qk . fmap, and rinv[p,i] = 1 / (2^12 ... sum_j E[p,i,j]) so that
- * softmax = E * rinv.  E: [P, N, Npad] fp16, Npad = round_up(N, 64).
- * sf_gma_aggregate computes out = fmap + gamma * ((E * rinv) . (W_v . fmap)^T) every iteration.        */
+ * heads = 1, dim = dim_head = d = 128 (the shipped model, core/models/streamflow.py:49).
+ * Q and K are constant over the refinement iterations, so sf_gma_attention computes ONCE per clip
+ *     E[p,i,j]   = fp16(2^12 * exp(s_ij - max_j s_ij)),   s = (scale * q) . k,   [q; k] = W_qk . fmap
+ *     rowsum[p,i] = sum_j E[p,i,j]                         (softmax = E / rowsum)
+ * with E stored as [P, N, Npad] fp16 (Npad = sf_gma_npad(N) = round_up(N, 64), pad columns zero), and
+ * sf_gma_aggregate computes every iteration
+ *     out = fmap + gamma * ((E / rowsum) . (W_v . fmap)^T).
+ * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) must be the SAME buffer for the attention call
+ * and all aggregate calls that use its E: it holds the fp32 accumulation buffer the aggregate keeps zeroed. */
 SF_API int64_t sf_gma_npad(int64_t N);
 SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);
 
-/* fmap: [P, C, N] (NCHW flattened, contiguous) of dtype fmap_dtype; w_qk: [2*d, C] fp32 contiguous.  */
+/* fmap: [P, C, N] (NCHW flattened, contiguous) of dtype fmap_dtype; w_qk: [2*d, C] fp32 contiguous
+ * (rows [0,d) -> q, rows [d,2d) -> k, as nn.Conv2d(dim, 2*inner, 1).weight chunked, core/gma.py:56).   */
 SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N,
-                     int64_t d, float scale, void* E, float* rinv, void* workspace, int64_t workspace_bytes,
+                     int64_t d, float scale, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
                      void* stream);
 
-/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] fp32; gamma: device pointer to 1 float;
+/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] fp32; gamma: DEVICE pointer to 1 float (no host sync);
  * out: [P, C, N] fp32 (requires C == d: the reference's `project` is None, core/gma.py:86-89).         */
-SF_API int sf_gma_aggregate(const void* E, const float* rinv, const void* fmap, int fmap_dtype, const float* w_v,
+SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const float* w_v,
                      const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d,
                      void* workspace, int64_t workspace_bytes, void* stream);
 

@@ -49,3 +49,37 @@ for (h, w, d) in [(46, 62, 256), (55, 128, 256)]:
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 20 * 1e3
     print(f"{h}x{w} lookup {us:.1f} us  -> {2904*h*w/us/1e3:.1f} GB/s algorithmic (L2-warm, single pair)")
+
+# ---------------------------------------------------------------- GMA
+from streamflow_b200 import Attention, Aggregate
+class _A: pass
+g = load_golden("gma_small.npz")
+att = Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+agg = Aggregate(args=_A(), dim=128, heads=1, dim_head=128).cuda()
+with torch.no_grad():
+    att.to_qk.weight.copy_(cuda(g["w_qk"]).view(256, 128, 1, 1)); agg.to_v.weight.copy_(cuda(g["w_v"]).view(128, 128, 1, 1)); agg.gamma.fill_(float(g["gamma"]))
+try:
+    h = att(cuda(g["inp"])); torch.cuda.synchronize()
+    attn = h.dense().cpu().numpy()
+    print(f"gma attn rel={rel_err(attn, g['attn']):.3e} nan={np.isnan(attn).sum()} rowsum_err={np.abs(attn.sum(-1)-1).max():.2e}")
+    out = agg(h, cuda(g["mf"])).cpu().numpy()
+    print(f"gma out rel={rel_err(out, g['out']):.3e} delta rel={rel_err(out-g['mf'], g['out']-g['mf']):.3e}")
+except Exception as e:
+    print("gma small FAILED:", e)
+try:
+    P, hh, ww = 3, 55, 128
+    inp = torch.relu(torch.randn(P, 128, hh, ww, device="cuda")); mf = torch.randn(P, 128, hh, ww, device="cuda")
+    for _ in range(2): h = att(inp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); h = att(inp); e1.record(); torch.cuda.synchronize()
+    print(f"sintel attention (once per clip): {e0.elapsed_time(e1)*1e3:.1f} us")
+    for _ in range(3): o = agg(h, mf)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10): o = agg(h, mf)
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 10 * 1e3
+    print(f"sintel aggregate per iter: {us:.1f} us -> E stream {P*7040*7040*2/us/1e3:.0f} GB/s")
+except Exception as e:
+    print("gma sintel FAILED:", e)

@@ -7,5 +7,8 @@ resolve to these classes so the unchanged StreamFlow model code runs on them).
 """
 from ._lib import StreamCorrError, lib  # noqa: F401
 from .corr import CorrBlock, CorrGroup, coords_grid  # noqa: F401
+from .gma import Aggregate, Attention, AttentionHandle  # noqa: F401
+from .install import install, uninstall  # noqa: F401
 
-__all__ = ["CorrBlock", "CorrGroup", "coords_grid", "StreamCorrError", "lib"]
+__all__ = ["CorrBlock", "CorrGroup", "coords_grid", "Attention", "Aggregate", "AttentionHandle", "install",
+           "uninstall", "StreamCorrError", "lib"]

@@ -29,16 +29,6 @@ LevelGeom make_level_geom(int64_t h, int64_t w) {
     return g;
 }
 
-namespace {
-
-inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-
-struct DeviceInfo {
-    int ok = -1;      // -1 unknown, 0 unusable, 1 usable
-    int sms = 0;
-    int dev = -1;
-};
-
 int query_device(DeviceInfo* out) {
     static thread_local DeviceInfo cache;
     int dev = -1;
@@ -67,6 +57,8 @@ int query_device(DeviceInfo* out) {
     return SF_OK;
 }
 
+namespace {
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -85,7 +77,8 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// rank-3 tiled map: dims / box innermost first; strides (bytes) for dims 1 and 2.
+}  // namespace
+
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what) {
     EncodeTiledFn fn = get_encode_fn();
@@ -108,6 +101,8 @@ int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_
     }
     return SF_OK;
 }
+
+namespace {
 
 int check_corr_shape(int64_t B, int64_t D, int64_t h, int64_t w) {
     SF_REQUIRE(B >= 1 && D >= 1 && h >= 1 && w >= 1, "corr: non-positive shape B=%lld D=%lld h=%lld w=%lld",

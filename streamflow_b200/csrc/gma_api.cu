@@ -1,17 +1,154 @@
-// TEMPORARY stub of the GMA entry points (replaced by the real implementation).
+// C ABI for the GMA path: sf_gma_attention (once per clip) and sf_gma_aggregate (every refinement iteration).
 #include "sf_internal.h"
+
+namespace sf {
+namespace {
+
+struct GmaWs {
+    int64_t q_off, k_off, rowmax_off, v_off, acc_off, total;
+    int Kp;
+    int64_t Npad;
+};
+
+GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
+    GmaWs ws{};
+    ws.Kp = static_cast<int>(3 * d);            // hi/lo split q, k: fp32-faithful logits (once per clip)
+    ws.Npad = align_up(N, 64);
+    int64_t off = 0;
+    ws.q_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
+    ws.k_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
+    ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
+    ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
+    ws.acc_off = off;     off += align_up(P * N * d * 4, 1024);
+    ws.total = off;
+    return ws;
+}
+
+int check_gma(int64_t P, int64_t C, int64_t N, int64_t d, const void* ws, int64_t ws_bytes, const GmaWs& lay) {
+    SF_REQUIRE(P >= 1 && N >= 1, "gma: non-positive shape P=%lld N=%lld", (long long)P, (long long)N);
+    SF_REQUIRE(d == 128 && C == 128,
+               "gma: kernels are specialised for heads=1, dim=dim_head=128 (the shipped model); got dim=%lld "
+               "dim_head=%lld -- no generic fallback",
+               (long long)C, (long long)d);
+    SF_REQUIRE(P * N < (1ll << 31), "gma: shape too large");
+    if (!ws || ws_bytes < lay.total) {
+        set_error("gma: workspace of %lld bytes needed, %lld given", (long long)lay.total, (long long)ws_bytes);
+        return SF_ERR_WORKSPACE;
+    }
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "gma: workspace must be 1024-byte aligned");
+    return SF_OK;
+}
+
+}  // namespace
+}  // namespace sf
+
 using namespace sf;
+
 extern "C" {
-int64_t sf_gma_npad(int64_t N) { return (N + 63) / 64 * 64; }
-int64_t sf_gma_workspace_bytes(int64_t, int64_t, int64_t, int64_t) { return 0; }
-int sf_gma_attention(const void*, int, const float*, int64_t, int64_t, int64_t, int64_t, float, void*, float*, void*,
-                     int64_t, void*) {
-    set_error("sf_gma_attention: not implemented yet");
-    return SF_ERR_INVALID;
+
+int64_t sf_gma_npad(int64_t N) { return align_up(N, 64); }
+
+int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d) {
+    (void)C;
+    if (P < 1 || N < 1 || d < 1) return 0;
+    return gma_ws_layout(P, N, d).total;
 }
-int sf_gma_aggregate(const void*, const float*, const void*, int, const float*, const float*, float*, int64_t, int64_t,
-                     int64_t, int64_t, void*, int64_t, void*) {
-    set_error("sf_gma_aggregate: not implemented yet");
-    return SF_ERR_INVALID;
+
+int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N, int64_t d,
+                     float scale, void* E, float* rowsum, void* workspace, int64_t workspace_bytes, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    const GmaWs ws = gma_ws_layout(P, N, d);
+    if (int rc = check_gma(P, C, N, d, workspace, workspace_bytes, ws)) return rc;
+    SF_REQUIRE(fmap && w_qk && E && rowsum, "gma_attention: null pointer argument");
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0, "gma_attention: E must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const int64_t Npad = ws.Npad;
+
+    GmaProjParams pq{};
+    pq.x = fmap; pq.x_dtype = fmap_dtype; pq.w = w_qk;
+    pq.P = (int)P; pq.C = (int)C; pq.N = (int)N; pq.O = 128;
+    pq.scale = scale;
+    pq.out = reinterpret_cast<__half*>(wsb + ws.q_off);
+    pq.out_batch_stride = N * ws.Kp; pq.ld = ws.Kp; pq.token_major = 1; pq.split = 1; pq.is_b = 0;
+    if (int rc = launch_gma_proj(pq, s)) return rc;
+    GmaProjParams pk = pq;
+    pk.w = w_qk + d * C; pk.scale = 1.0f;
+    pk.out = reinterpret_cast<__half*>(wsb + ws.k_off); pk.is_b = 1;
+    if (int rc = launch_gma_proj(pk, s)) return rc;
+
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
+    SF_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, P * N * 4, s));
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.acc_off, 0, P * N * d * 4, s));
+
+    CUtensorMap tm_q, tm_k, tm_e;
+    const uint64_t kp = static_cast<uint64_t>(ws.Kp);
+    if (int rc = make_tmap3(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.q_off, kp, N, P, kp * 2, N * kp * 2, 64,
+                            128, "Q"))
+        return rc;
+    if (int rc = make_tmap3(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.k_off, kp, N, P, kp * 2, N * kp * 2, 64,
+                            256, "K"))
+        return rc;
+    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, Npad, N, P, Npad * 2, N * Npad * 2, 64, 32,
+                            "E(store)"))
+        return rc;
+
+    GmaStatsParams sp{};
+    sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = ws.Kp;
+    sp.m_tiles = (int)((N + 127) / 128);
+    sp.n_tiles = (int)((N + 255) / 256);
+    const int64_t base_units = P * sp.m_tiles;
+    int chunks = (int)((4ll * di.sms + base_units - 1) / base_units);
+    sp.chunks = std::max(1, std::min(chunks, sp.n_tiles));
+    sp.rowmax_bits = reinterpret_cast<unsigned*>(wsb + ws.rowmax_off);
+    sp.rowsum = rowsum;
+    sp.E = static_cast<__half*>(E);
+    sp.pass = 1;
+    if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
+    sp.pass = 2;
+    return launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s);
 }
+
+int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const float* w_v,
+                     const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    const GmaWs ws = gma_ws_layout(P, N, d);
+    if (int rc = check_gma(P, C, N, d, workspace, workspace_bytes, ws)) return rc;
+    SF_REQUIRE(E && rowsum && fmap && w_v && gamma && out, "gma_aggregate: null pointer argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    const int64_t Npad = ws.Npad;
+
+    GmaProjParams pv{};
+    pv.x = fmap; pv.x_dtype = fmap_dtype; pv.w = w_v;
+    pv.P = (int)P; pv.C = (int)C; pv.N = (int)N; pv.O = 128;
+    pv.scale = 1.0f;
+    pv.out = reinterpret_cast<__half*>(wsb + ws.v_off);
+    pv.out_batch_stride = d * Npad; pv.ld = (int)Npad; pv.token_major = 0; pv.split = 0; pv.is_b = 0;
+    if (int rc = launch_gma_proj(pv, s)) return rc;
+
+    CUtensorMap tm_e, tm_v;
+    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, Npad, N, P, Npad * 2, N * Npad * 2, 64, 128,
+                            "E(load)"))
+        return rc;
+    if (int rc = make_tmap3(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.v_off, Npad, d, P, Npad * 2,
+                            d * Npad * 2, 64, 128, "V"))
+        return rc;
+
+    GmaAggParams ap{};
+    ap.P = (int)P; ap.N = (int)N; ap.Npad = (int)Npad; ap.C = (int)C;
+    ap.m_tiles = (int)((N + 127) / 128);
+    ap.k_blocks = (int)(Npad / 64);
+    ap.acc = reinterpret_cast<float*>(wsb + ws.acc_off);
+    ap.rowsum = rowsum;
+    ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
+    ap.gamma = gamma;
+    ap.out = out;
+    if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
+    return launch_gma_finalize(ap, s);
 }
+
+}  // extern "C"

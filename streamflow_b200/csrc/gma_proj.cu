@@ -1,0 +1,173 @@
+// 1x1-convolution projections of GMA (to_qk, core/gma.py:47,56; to_v, core/gma.py:80,94) as a small
+// tensor-core GEMM:  out[o, n] = scale * sum_c W[o, c] * X[c, n]   (X = NCHW feature map, n = y*w + x).
+//
+// 0.23 GFLOP per map: latency-, not throughput-critical, so this uses the warp-level mma.sync path
+// (m16n8k16, fp16 in / fp32 accumulate) with ldmatrix.trans for the n-contiguous X operand.  Results are
+// written in the layouts the tcgen05 kernels consume through TMA:
+//   token-major   [P, N, ld]    (q, k; optionally hi/lo split along K for fp32-faithful logits)
+//   channel-major [P, O, ld]    (v; ld = Npad, pad columns written as zero)
+#include <cuda_bf16.h>
+
+#include "sf_internal.h"
+
+namespace sf {
+
+namespace {
+
+constexpr int kTok = 64;          // tokens per CTA
+constexpr int kXPad = kTok + 8;   // Xs row pitch (halfs): 144 B rows keep ldmatrix conflict-free
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p) {
+    return static_cast<float>(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) {
+    return __half2float(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(*p);
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned& r0, unsigned& r1, unsigned& r2, unsigned& r3,
+                                                  const void* smem_ptr) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(a));
+}
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// CTA: 256 threads = 8 warps; tile = 128 outputs x 64 tokens; warp w owns outputs [16w, 16w+16).
+// Requires O == 128 per launch (rows o0..o0+127 of W), C % 16 == 0, C <= 256.
+template <typename T>
+__global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ GmaProjParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int C = p.C;
+    const int wpad = C + 8;
+    __half* Xs = reinterpret_cast<__half*>(smem);                    // [C][kXPad]
+    __half* Ws = Xs + C * kXPad;                                     // [128][C + 8]
+    __half* Ds = Ws + 128 * wpad;                                    // staging, 128 x 72 or 64 x 136
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * kTok;
+    const int pb = blockIdx.y;
+    const T* X = reinterpret_cast<const T*>(p.x) + static_cast<long long>(pb) * C * p.N;
+
+    for (int i = tid; i < C * (kTok / 4); i += 256) {
+        const int c = i / (kTok / 4), n4 = (i - c * (kTok / 4)) * 4;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = n0 + n4 + e;
+            v[e] = (n < p.N) ? load_as_float<T>(X + static_cast<long long>(c) * p.N + n) : 0.f;
+        }
+        __half2* d = reinterpret_cast<__half2*>(Xs + c * kXPad + n4);
+        d[0] = __floats2half2_rn(v[0], v[1]);
+        d[1] = __floats2half2_rn(v[2], v[3]);
+    }
+    for (int i = tid; i < 128 * (C / 2); i += 256) {
+        const int o = i / (C / 2), c2 = (i - o * (C / 2)) * 2;
+        const float2 w = *reinterpret_cast<const float2*>(p.w + static_cast<long long>(o) * C + c2);
+        *reinterpret_cast<__half2*>(Ws + o * wpad + c2) = __floats2half2_rn(w.x, w.y);
+    }
+    __syncthreads();
+
+    float acc[8][4] = {};
+    const int g = lane >> 2, t = lane & 3;
+    const __half* wrow = Ws + (warp * 16 + g) * wpad;
+    for (int k0 = 0; k0 < C; k0 += 16) {
+        unsigned a[4];
+        a[0] = *reinterpret_cast<const unsigned*>(wrow + k0 + 2 * t);
+        a[1] = *reinterpret_cast<const unsigned*>(wrow + 8 * wpad + k0 + 2 * t);
+        a[2] = *reinterpret_cast<const unsigned*>(wrow + k0 + 8 + 2 * t);
+        a[3] = *reinterpret_cast<const unsigned*>(wrow + 8 * wpad + k0 + 8 + 2 * t);
+#pragma unroll
+        for (int jt = 0; jt < 8; jt += 2) {
+            // matrices: (k 0-7, tile jt) (k 8-15, tile jt) (k 0-7, tile jt+1) (k 8-15, tile jt+1)
+            const int mat = lane >> 3, r = lane & 7;
+            const __half* src = Xs + (k0 + (mat & 1) * 8 + r) * kXPad + (jt + (mat >> 1)) * 8;
+            unsigned b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, src);
+            mma_16816(acc[jt], a, b0, b1);
+            mma_16816(acc[jt + 1], a, b2, b3);
+        }
+    }
+
+    // D fragment: acc[jt][0..1] -> (o = 16w + g, n = 8jt + 2t, +1); acc[jt][2..3] -> o + 8
+    const int parts = (p.token_major && p.split) ? 3 : 1;
+    for (int part = 0; part < parts; ++part) {
+        __syncthreads();   // Ds reuse (and Xs/Ws reads finished on the first pass)
+#pragma unroll
+        for (int jt = 0; jt < 8; ++jt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int o = warp * 16 + g + (e >> 1) * 8;
+                const int n = jt * 8 + 2 * t + (e & 1);
+                const float v = acc[jt][e] * p.scale;
+                const __half hi = __float2half_rn(v);
+                __half val = hi;
+                if (part > 0) {
+                    const bool want_lo = (part == 1) == (p.is_b != 0);     // B: [hi | lo | hi'], A: [hi | hi' | lo]
+                    val = want_lo ? __float2half_rn((v - __half2float(hi)) * 2048.f)
+                                  : __float2half_rn(__half2float(hi) * (1.f / 2048.f));
+                }
+                if (p.token_major)
+                    Ds[n * 136 + o] = val;
+                else
+                    Ds[o * kXPad + n] = val;
+            }
+        __syncthreads();
+        if (p.token_major) {      // rows = tokens, 128 outputs = 256 B per row
+            __half* out = p.out + static_cast<long long>(pb) * p.out_batch_stride + part * 128;
+            for (int i = tid; i < kTok * 16; i += 256) {
+                const int n = i >> 4, seg = i & 15;
+                if (n0 + n < p.N)
+                    *reinterpret_cast<int4*>(out + static_cast<long long>(n0 + n) * p.ld + seg * 8) =
+                        *reinterpret_cast<const int4*>(Ds + n * 136 + seg * 8);
+            }
+        } else {                  // rows = outputs, 64 tokens = 128 B per row; pad columns get the zeros
+            __half* out = p.out + static_cast<long long>(pb) * p.out_batch_stride;
+            for (int i = tid; i < 128 * 8; i += 256) {
+                const int o = i >> 3, seg = i & 7;
+                if (n0 + seg * 8 < p.ld)
+                    *reinterpret_cast<int4*>(out + static_cast<long long>(o) * p.ld + n0 + seg * 8) =
+                        *reinterpret_cast<const int4*>(Ds + o * kXPad + seg * 8);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
+    SF_REQUIRE(p.O == 128, "gma_proj: 128 output channels per launch (got %d)", p.O);
+    SF_REQUIRE(p.C % 16 == 0 && p.C >= 16 && p.C <= 256, "gma_proj: C must be a multiple of 16 in [16, 256] (got %d)",
+               p.C);
+    SF_REQUIRE(p.ld % 8 == 0, "gma_proj: output pitch must be a multiple of 8");
+    const int smem = (p.C * kXPad + 128 * (p.C + 8) + 128 * kXPad) * 2;
+    const int cols = p.token_major ? p.N : p.ld;
+    dim3 grid((cols + kTok - 1) / kTok, p.P);
+    auto launch = [&](auto kernel) -> int {
+        SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kernel<<<grid, 256, smem, s>>>(p);
+        SF_CUDA_CHECK(cudaGetLastError());
+        return SF_OK;
+    };
+    switch (p.x_dtype) {
+        case SF_DT_F32: return launch(gma_proj_kernel<float>);
+        case SF_DT_F16: return launch(gma_proj_kernel<__half>);
+        case SF_DT_BF16: return launch(gma_proj_kernel<__nv_bfloat16>);
+        default: set_error("gma_proj: unsupported dtype %d", p.x_dtype); return SF_ERR_INVALID;
+    }
+}
+
+}  // namespace sf

@@ -1,0 +1,497 @@
+// G3: GMA softmax attention (core/gma.py:53-65) and motion-feature aggregation (core/gma.py:91-104) on
+// tcgen05 tensor cores.
+//
+// Q and K do not change across refinement iterations, so the softmax numerator is computed ONCE per clip and
+// kept in HBM as fp16 (E = 2^12 * exp(s - rowmax), [P, N, Npad], 99 MB per Sintel map -- trivial against 180 GB),
+// exactly the matrix the reference's autocast path re-casts to fp16 every iteration (core/gma.py:95-97).
+// Every iteration is then one streaming GEMM  acc = E . V^T  bound by reading E from HBM:
+//
+//   gma_stats_kernel      S = Q K^T tiles (128 x 256, K = d or 3d for hi/lo-split operands) in TMEM;
+//                         pass 1 reduces the row max, pass 2 writes E with TMA stores and the row sums.
+//   gma_aggregate_kernel  stream-K partition of all (map, query-tile, key-block) work over the SMs so every SM
+//                         streams the same number of bytes; partial 128 x 128 tiles are reduced with vector
+//                         red.global.add into an fp32 buffer.
+//   gma_finalize_kernel   out = fmap + gamma * acc / rowsum  (transposing [N, C] -> NCHW) and re-zeroes acc.
+#include <cuda_bf16.h>
+
+#include "sf_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace sf {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kEScale = 4096.f;     // E = 2^12 * exp(.): keeps small weights out of the fp16 subnormals
+
+__device__ __forceinline__ unsigned enc_ordered(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// =====================================================================================================
+// stats: S = Q K^T
+// =====================================================================================================
+namespace st {
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kEpiBuf = 32 * 128;                       // 32 rows x 64 fp16
+constexpr int kEpiBytes = 4 * 2 * kEpiBuf;
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
+constexpr int kTmemCols = 512;
+}  // namespace st
+
+struct GmaStatsArgs {
+    CUtensorMap tm_q, tm_k, tm_e;
+    GmaStatsParams p;
+};
+
+__global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
+    using namespace st;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tfull = bars + 2 * kStages;
+    uint64_t* tempty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const GmaStatsParams& p = args.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = (p.Kp + BK - 1) / BK;
+    const int per_chunk = (p.n_tiles + p.chunks - 1) / p.chunks;
+    const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
+    const long long u_begin = units * blockIdx.x / gridDim.x;
+    const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.tm_q);
+        tma_prefetch_desc(&args.tm_k);
+        tma_prefetch_desc(&args.tm_e);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto unit_coords = [&](long long u, int& pb, int& mt, int& nt0, int& nt1) {
+        const int per_p = p.m_tiles * p.chunks;
+        pb = static_cast<int>(u / per_p);
+        const int r = static_cast<int>(u - static_cast<long long>(pb) * per_p);
+        mt = r / p.chunks;
+        const int ck = r - mt * p.chunks;
+        nt0 = ck * per_chunk;
+        nt1 = min(p.n_tiles, nt0 + per_chunk);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = u_begin; u < u_end; ++u) {
+                int pb, mt, nt0, nt1;
+                unit_coords(u, pb, mt, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = stage_base + stage * kStageBytes;
+                        mbar_expect_tx(&full[stage], kStageBytes);
+                        tma_load_3d(&args.tm_q, &full[stage], sa, kb * BK, mt * BM, pb);
+                        tma_load_3d(&args.tm_k, &full[stage], sa + kABytes, kb * BK, nt * BN, pb);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            int stage = 0, local = 0;
+            uint32_t phase = 0;
+            for (long long u = u_begin; u < u_end; ++u) {
+                int pb, mt, nt0, nt1;
+                unit_coords(u, pb, mt, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt, ++local) {
+                    const int acc = local & 1;
+                    mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+                        const uint64_t da = make_kmajor_sw128_desc(sa);
+                        const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit(&empty[stage]);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tfull[acc]);
+                }
+            }
+        }
+    } else {
+        const int e = warp - 2, quad = warp & 3;
+        uint8_t* bufs = epi_base + e * 2 * kEpiBuf;
+        int local = 0, buf_sel = 0;
+        for (long long u = u_begin; u < u_end; ++u) {
+            int pb, mt, nt0, nt1;
+            unit_coords(u, pb, mt, nt0, nt1);
+            const int row = mt * BM + quad * 32 + lane;
+            const bool row_ok = row < p.N;
+            const long long ridx = static_cast<long long>(pb) * p.N + row;
+            float run_max = -INFINITY, run_sum = 0.f, mrow = 0.f;
+            if (p.pass == 2 && row_ok) mrow = dec_ordered(p.rowmax_bits[ridx]) * kLog2e;
+            for (int nt = nt0; nt < nt1; ++nt, ++local) {
+                const int acc = local & 1;
+                mbar_wait(&tfull[acc], (local >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cp = 0; cp < BN / 64; ++cp) {      // pairs of 32-column chunks = 64 keys
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr =
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cp * 64;
+                    tmem_ld_32x32(taddr, v0);
+                    tmem_ld_32x32(taddr + 32, v1);
+                    tmem_ld_wait();
+                    if (cp == BN / 64 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    const int col0 = nt * BN + cp * 64;
+                    if (col0 >= p.Npad) continue;
+                    if (p.pass == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (col0 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v0[j]));
+                            if (col0 + 32 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v1[j]));
+                        }
+                    } else {
+                        uint8_t* buf = bufs + buf_sel * kEpiBuf;
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                        __half2 h[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float a0 = (col0 + j < p.N)
+                                                 ? exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                            const float a1 = (col0 + j + 1 < p.N)
+                                                 ? exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                            const float b0 = (col0 + 32 + j < p.N)
+                                                 ? exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                            const float b1 = (col0 + 32 + j + 1 < p.N)
+                                                 ? exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                            h[j >> 1] = __floats2half2_rn(a0, a1);
+                            h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 f = __half22float2(h[j]);
+                            run_sum += f.x + f.y;
+                        }
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row
+                            int4 o;
+                            o.x = *reinterpret_cast<int*>(&h[c16 * 4 + 0]);
+                            o.y = *reinterpret_cast<int*>(&h[c16 * 4 + 1]);
+                            o.z = *reinterpret_cast<int*>(&h[c16 * 4 + 2]);
+                            o.w = *reinterpret_cast<int*>(&h[c16 * 4 + 3]);
+                            *reinterpret_cast<int4*>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_3d(&args.tm_e, buf, col0, mt * BM + quad * 32, pb);
+                            tma_store_commit();
+                        }
+                        buf_sel ^= 1;
+                    }
+                }
+            }
+            if (row_ok) {
+                if (p.pass == 1)
+                    atomicMax(p.rowmax_bits + ridx, enc_ordered(run_max));
+                else
+                    atomicAdd(p.rowsum + ridx, run_sum);
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// =====================================================================================================
+// aggregate: acc[p, n, c] += sum_j E[p, n, j] * V[p, c, j]     (stream-K)
+// =====================================================================================================
+namespace ag {
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 6;
+constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kTmemCols = 256;
+}  // namespace ag
+
+struct GmaAggArgs {
+    CUtensorMap tm_e, tm_v;
+    GmaAggParams p;
+};
+
+__global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
+    using namespace ag;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tfull = bars + 2 * kStages;
+    uint64_t* tempty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const GmaAggParams& p = args.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long KB = p.k_blocks;
+    const long long work = static_cast<long long>(p.P) * p.m_tiles * KB;
+    const long long w_begin = work * blockIdx.x / gridDim.x;
+    const long long w_end = work * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.tm_e);
+        tma_prefetch_desc(&args.tm_v);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long pos = w_begin; pos < w_end; ++pos) {
+                const long long tile = pos / KB;
+                const int kb = static_cast<int>(pos - tile * KB);
+                const int pb = static_cast<int>(tile / p.m_tiles);
+                const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = stage_base + stage * kStageBytes;
+                mbar_expect_tx(&full[stage], kStageBytes);
+                tma_load_3d_hint(&args.tm_e, &full[stage], sa, kb * BK, mt * BM, pb, kEvictFirst);
+                tma_load_3d_hint(&args.tm_v, &full[stage], sa + kABytes, kb * BK, 0, pb, kEvictLast);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            int stage = 0, local = 0;
+            uint32_t phase = 0;
+            long long pos = w_begin;
+            while (pos < w_end) {
+                const long long tile = pos / KB;
+                const long long seg_end = min(w_end, (tile + 1) * KB);
+                const int acc = local & 1;
+                mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                bool first = true;
+                for (; pos < seg_end; ++pos) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+                    const uint64_t da = make_kmajor_sw128_desc(sa);
+                    const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    first = false;
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[acc]);
+                ++local;
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        int local = 0;
+        long long pos = w_begin;
+        while (pos < w_end) {
+            const long long tile = pos / KB;
+            const long long seg_end = min(w_end, (tile + 1) * KB);
+            const int pb = static_cast<int>(tile / p.m_tiles);
+            const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
+            const int acc = local & 1;
+            mbar_wait(&tfull[acc], (local >> 1) & 1);
+            tc_fence_after();
+            const int row = mt * BM + quad * 32 + lane;
+            float* dst = p.acc + (static_cast<long long>(pb) * p.N + row) * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + ch * 32, v);
+                tmem_ld_wait();
+                if (ch == BN / 32 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                if (row < p.N) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + ch * 32 + 4 * j),
+                                     "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                                     "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                                     : "memory");
+                }
+            }
+            pos = seg_end;
+            ++local;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// out[p, c, n] = fmap[p, c, n] + gamma * acc[p, n, c] / rowsum[p, n];  acc <- 0.   block (32, 8)
+template <typename T>
+__global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, pb = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    float* acc = p.acc + static_cast<long long>(pb) * p.N * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty + 8 * i;
+        float v = 0.f;
+        if (n < p.N) {
+            float* a = acc + static_cast<long long>(n) * 128 + c0 + tx;
+            v = *a;
+            *a = 0.f;
+        }
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+    const float gamma = __ldg(p.gamma);
+    const int n = n0 + tx;
+    if (n >= p.N) return;
+    const float rinv = 1.0f / __ldg(p.rowsum + static_cast<long long>(pb) * p.N + n);
+    const T* fm = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(pb) * p.C * p.N;
+    float* out = p.out + static_cast<long long>(pb) * p.C * p.N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i;
+        const long long idx = static_cast<long long>(c) * p.N + n;
+        out[idx] = static_cast<float>(fm[idx]) + gamma * (tile[tx][ty + 8 * i] * rinv);
+    }
+}
+
+__global__ void fill_u32_kernel(unsigned* p, unsigned v, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace
+
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
+                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s) {
+    GmaStatsArgs args;
+    args.tm_q = tm_q;
+    args.tm_k = tm_k;
+    args.tm_e = tm_e;
+    args.p = p;
+    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kSmemBytes));
+    const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
+    const int grid = static_cast<int>(std::min<long long>(units, num_sms));
+    gma_stats_kernel<<<grid, 192, st::kSmemBytes, s>>>(args);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
+                         cudaStream_t s) {
+    GmaAggArgs args;
+    args.tm_e = tm_e;
+    args.tm_v = tm_v;
+    args.p = p;
+    SF_CUDA_CHECK(
+        cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ag::kSmemBytes));
+    const long long work = static_cast<long long>(p.P) * p.m_tiles * p.k_blocks;
+    const int grid = static_cast<int>(std::min<long long>(work, num_sms));
+    gma_aggregate_kernel<<<grid, 192, ag::kSmemBytes, s>>>(args);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
+    dim3 grid((p.N + 31) / 32, p.C / 32, p.P);
+    switch (p.fmap_dtype) {
+        case SF_DT_F32: gma_finalize_kernel<float><<<grid, dim3(32, 8), 0, s>>>(p); break;
+        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, dim3(32, 8), 0, s>>>(p); break;
+        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, s>>>(p); break;
+        default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
+    }
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s) {
+    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 1184));
+    fill_u32_kernel<<<blocks, 256, 0, s>>>(ptr, value, n);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+}  // namespace sf

@@ -35,6 +35,18 @@ struct LevelGeom {
 };
 LevelGeom make_level_geom(int64_t h, int64_t w);
 
+struct DeviceInfo {
+    int ok = -1;      // -1 unknown, 0 unusable, 1 usable
+    int sms = 0;
+    int dev = -1;
+};
+// SF_OK and fills `out` when the current device is sm_100; SF_ERR_NODEVICE (with message) otherwise.
+int query_device(DeviceInfo* out);
+// rank-3 tiled TMA map, 128B swizzle: dims / box innermost first; strides (bytes) of dims 1 and 2; box[2] = 1.
+int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what);
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
 // Power-of-two operand scale derived from a tensor's absmax (bits of a non-negative float):
 // amax * 2^e lands in [2^13, 2^14) so fp16 never overflows; e is clamped to [-40, 40].
 __host__ __device__ inline int scale_exponent_from_bits(unsigned bits) {
@@ -122,8 +134,8 @@ struct GmaStatsParams {
     __half* E;                  // [P, N, Npad]
     int pass;
 };
-int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k, int num_sms,
-                     cudaStream_t s);
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
+                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s);
 
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128

@@ -1,0 +1,133 @@
+"""Drop-in replacement for ``Attention`` / ``Aggregate`` of the reference's ``core/gma.py`` (sm_100a).
+
+Same constructors, parameter names and call signatures as the reference (``core/gma.py:34-104``), so
+reference checkpoints load unchanged (``to_qk.weight [2*inner, dim, 1, 1]``, ``to_v.weight [inner, dim, 1, 1]``,
+``gamma [1]``) and ``core/models/streamflow.py:124`` / ``core/update.py:769`` run unmodified:
+
+    attn = Attention(args=..., dim=128, heads=1, max_pos_size=160, dim_head=128)(inps)
+    out  = Aggregate(args=..., dim=128, heads=1, dim_head=128)(attn, motion_features)
+
+``Attention.forward`` returns an opaque ``AttentionHandle`` instead of the dense ``[P, 1, N, N]`` fp32 matrix
+(the callers only pass it on to ``Aggregate``): it owns the fp16 softmax numerators E, their row sums and the
+workspace.  ``handle.dense()`` materialises the reference-shaped matrix for tests.
+
+The kernels are specialised for the shipped configuration heads=1, dim=dim_head=128; anything else raises
+(there is no eager fallback).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import StreamCorrError
+from .corr import _aligned_workspace, _stream_ptr
+
+
+class AttentionHandle:
+    """What ``Attention.forward`` returns: E [P, N, Npad] fp16, rowsum [P, N] fp32 and the workspace."""
+
+    def __init__(self, E, rowsum, ws_buf, ws_ptr, ws_bytes, shape):
+        self.E, self.rowsum = E, rowsum
+        self._ws_buf, self._ws_ptr, self._ws_bytes = ws_buf, ws_ptr, ws_bytes
+        self.P, self.C, self.h, self.w = shape
+        self.N = self.h * self.w
+
+    @property
+    def shape(self):
+        return (self.P, 1, self.N, self.N)
+
+    def dense(self):
+        """Reference-shaped softmax matrix [P, 1, N, N] fp32 (test helper; O(N^2) memory)."""
+        return (self.E[:, :, : self.N].float() / self.rowsum[:, :, None])[:, None]
+
+
+def _check_cfg(dim, heads, dim_head):
+    if heads != 1 or dim != 128 or dim_head != 128:
+        raise StreamCorrError(
+            f"GMA kernels are specialised for heads=1, dim=dim_head=128 (got heads={heads}, dim={dim}, "
+            f"dim_head={dim_head}); no fallback path exists")
+
+
+class Attention(nn.Module):
+    def __init__(self, *, args, dim, max_pos_size=100, heads=4, dim_head=128):
+        super().__init__()
+        self.args = args
+        self.heads = heads
+        self.dim = dim
+        self.dim_head = dim_head
+        self.scale = dim_head ** -0.5
+        inner_dim = heads * dim_head
+        self.to_qk = nn.Conv2d(dim, inner_dim * 2, 1, bias=False)
+
+    def forward(self, fmap):
+        _check_cfg(self.dim, self.heads, self.dim_head)
+        if fmap.dim() != 4 or fmap.shape[1] != self.dim:
+            raise StreamCorrError(f"Attention expects [P, {self.dim}, h, w], got {tuple(fmap.shape)}")
+        if not fmap.is_cuda:
+            raise StreamCorrError("Attention needs a CUDA tensor (no CPU fallback)")
+        x = fmap.detach()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        P, C, h, w = x.shape
+        N = h * w
+        dev = x.device
+        L = _lib.lib()
+        wq = self.to_qk.weight.detach().reshape(2 * self.dim_head, C)
+        if wq.dtype != torch.float32 or not wq.is_contiguous():
+            wq = wq.float().contiguous()
+        with torch.cuda.device(dev):
+            npad = L.sf_gma_npad(N)
+            E = torch.empty((P, N, npad), dtype=torch.float16, device=dev)
+            rowsum = torch.empty((P, N), dtype=torch.float32, device=dev)
+            ws_bytes = L.sf_gma_workspace_bytes(P, C, N, self.dim_head)
+            ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
+            rc = L.sf_gma_attention(x.data_ptr(), _lib.torch_dtype_code(x.dtype), wq.data_ptr(), P, C, N,
+                                    self.dim_head, float(self.scale), E.data_ptr(), rowsum.data_ptr(), ws_ptr,
+                                    ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "sf_gma_attention")
+        return AttentionHandle(E, rowsum, ws_buf, ws_ptr, ws_bytes, (P, C, h, w))
+
+
+class Aggregate(nn.Module):
+    def __init__(self, args, dim, heads=4, dim_head=128):
+        super().__init__()
+        self.args = args
+        self.heads = heads
+        self.dim = dim
+        self.dim_head = dim_head
+        self.scale = dim_head ** -0.5
+        inner_dim = heads * dim_head
+        self.to_v = nn.Conv2d(dim, inner_dim, 1, bias=False)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        if dim != inner_dim:
+            self.project = nn.Conv2d(inner_dim, dim, 1, bias=False)
+        else:
+            self.project = None
+
+    def forward(self, attn, fmap):
+        _check_cfg(self.dim, self.heads, self.dim_head)
+        if not isinstance(attn, AttentionHandle):
+            raise StreamCorrError("Aggregate expects the handle returned by streamflow_b200.gma.Attention")
+        if fmap.dim() != 4 or tuple(fmap.shape) != (attn.P, self.dim, attn.h, attn.w):
+            raise StreamCorrError(f"Aggregate expects fmap [{attn.P}, {self.dim}, {attn.h}, {attn.w}], "
+                                  f"got {tuple(fmap.shape)}")
+        x = fmap.detach()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        P, C, h, w = x.shape
+        dev = x.device
+        wv = self.to_v.weight.detach().reshape(self.dim_head, C)
+        if wv.dtype != torch.float32 or not wv.is_contiguous():
+            wv = wv.float().contiguous()
+        gamma = self.gamma.detach()
+        if gamma.dtype != torch.float32:
+            gamma = gamma.float()
+        with torch.cuda.device(dev):
+            out = torch.empty((P, C, h, w), dtype=torch.float32, device=dev)
+            rc = _lib.lib().sf_gma_aggregate(attn.E.data_ptr(), attn.rowsum.data_ptr(), x.data_ptr(),
+                                             _lib.torch_dtype_code(x.dtype), wv.data_ptr(), gamma.data_ptr(),
+                                             out.data_ptr(), P, C, attn.N, self.dim_head, attn._ws_ptr,
+                                             attn._ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "sf_gma_aggregate")
+        return out
