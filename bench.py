@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- StreamFlow correlation/GMA hot path on B200: flow frames/s + kernel rooflines.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "Config 2", operator-level synthetic): one T=4 clip at
+Sintel 436x1024 (padded 440x1024 -> 55x128 at 1/8, N = 7040, D = 256, 3 frame pairs) per GPU, 12 refinement
+iterations.  One STEP = one pass of the hot path over one clip per rank:
+    3 x CorrBlock build  +  1 x Attention  +  12 x (3-pair lookup + Aggregate)
+(core/models/streamflow.py:110,124,132 and core/update.py:769).  Clips are independent, so ranks shard clips
+with no data-path collective (weak scaling); the only collective is the timing reduction.
+
+JSON line (rank 0): value = flow fields per second over all ranks with inputs resident in HBM; e2e = the same
+through the public Python/C-ABI call path with pinned HOST buffers (H2D of every input and D2H of the results
+inside the timed region); roofline = dominant kernel (GMA aggregate, HBM-bound E stream) measured with CUDA
+events around the kernel launches inside the timed region; kernels = the same for lookup / corr GEMM;
+cpu_baseline = the torch-CPU port of the reference path on this host's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H8, W8, D, T, ITERS, CDIM = 55, 128, 256, 4, 12, 128
+N = H8 * W8
+PAIRS = T - 1
+METRIC = "flow frames/s (Sintel 436x1024, T=4, 12 iters); corr-lookup HBM GB/s"
+WORKLOAD = "sintel_436x1024_T4_12iters_hotpath"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def make_inputs(seed: int):
+    """Synthetic clip, identical on every arm (torch CPU generator)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    # fnet output under mixed precision: fp16 values upcast to fp32, channels-last storage (streamflow.py:107)
+    fm = torch.randn(1, T, H8, W8, D, generator=g).half().float()
+    inps = torch.relu(torch.randn(PAIRS, CDIM, H8, W8, generator=g))
+    mfs = torch.randn(PAIRS, CDIM, H8, W8, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H8), torch.arange(W8), indexing="ij")
+    grid = torch.stack((xs, ys), 0).float()[None, None]                       # [1,1,2,h,w]
+    walk = torch.cumsum(torch.randn(ITERS, PAIRS, 1, 2, H8, W8, generator=g) * 5.0 / ITERS ** 0.5, 0)
+    coords = (grid + walk).contiguous()                                       # [iters, pairs, 1, 2, h, w]
+    w_qk = torch.randn(2 * CDIM, CDIM, generator=g) * (CDIM ** -0.5) * 2.0
+    w_v = torch.randn(CDIM, CDIM, generator=g) * (CDIM ** -0.5)
+    return {"fm_nhwc": fm, "inps": inps, "mfs": mfs, "coords": coords, "w_qk": w_qk, "w_v": w_v, "gamma": 0.8}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.15)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    import torch
+    from oracle import torch_port as tp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = make_inputs(0)
+    fmaps = inp["fm_nhwc"].permute(0, 1, 4, 2, 3)
+    coords = inp["coords"]
+
+    def step():
+        return tp.cpu_hot_path(fmaps, coords, inp["inps"], inp["mfs"], inp["w_qk"], inp["w_v"], inp["gamma"])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = PAIRS / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "flow frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (torch CPU port of "
+                   "core/corr.py + core/gma.py; the reference checkout cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": val, "unit": "flow frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps (1 clip: 3 builds + attention + 12 x (3 lookups + aggregate))"},
+        "e2e": {"value": val, "unit": "flow frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------- our arm (GPU)
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import streamflow_b200 as sfb
+    from streamflow_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = sfb.lib()
+    peaks = load_peaks()
+
+    class _A:
+        pass
+
+    host = make_inputs(rank)                      # each rank owns a different clip (weak scaling)
+    att = sfb.Attention(args=_A(), dim=CDIM, heads=1, max_pos_size=160, dim_head=CDIM).to(dev)
+    agg = sfb.Aggregate(args=_A(), dim=CDIM, heads=1, dim_head=CDIM).to(dev)
+    with torch.no_grad():
+        att.to_qk.weight.copy_(host["w_qk"].view(2 * CDIM, CDIM, 1, 1))
+        agg.to_v.weight.copy_(host["w_v"].view(CDIM, CDIM, 1, 1))
+        agg.gamma.fill_(host["gamma"])
+
+    pinned = {k: host[k].pin_memory() for k in ("fm_nhwc", "inps", "mfs", "coords")}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    out_feats_host = torch.empty((PAIRS, 324, H8, W8), dtype=torch.float32).pin_memory()
+    out_agg_host = torch.empty((PAIRS, CDIM, H8, W8), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    d2h = out_feats_host.numel() * 4 + out_agg_host.numel() * 4
+
+    def hot_path(t):
+        """The hot path for one clip through the public API (what core/models/streamflow.py drives)."""
+        fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)                         # [1, T, D, h, w] channels-last views
+        blocks = [sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4) for i in range(PAIRS)]
+        group = sfb.CorrGroup(blocks)
+        handle = att(t["inps"])
+        feats = out = None
+        for it in range(ITERS):
+            feats = group([t["coords"][it, i] for i in range(PAIRS)])
+            out = agg(handle, t["mfs"])
+        return feats, out
+
+    def step_resident():
+        return hot_path(resident)
+
+    def step_e2e():
+        t = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        feats, out = hot_path(t)
+        out_feats_host.copy_(feats, non_blocking=True)
+        out_agg_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_steps(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    # ---- headline: device-resident inputs
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.sf_launch_count()
+    if sampler:
+        sampler.start()
+    ms_step = time_steps(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    launches = (L.sf_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region
+    ms_e2e = time_steps(step_e2e, args.steps, max(args.warmup, 3))
+
+    # ---- per-kernel event timing inside a timed region of `steps` steps
+    def kernel_time(which):
+        """Mean duration (us) of kernel `which`, one CUDA-event pair per launch, over timed steps."""
+        durs = [_step_with_kernel_events(which) for _ in range(max(3, min(args.steps, 5)))]
+        flat = [d for ds in durs[1:] for d in ds]
+        return sum(flat) / len(flat), len(flat)
+
+    def _raw_event():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()          # forces creation of the underlying cudaEvent_t
+        return ev
+
+    def _step_with_kernel_events(which):
+        t = resident
+        fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)
+        pairs = []
+
+        def arm():
+            a, b = _raw_event(), _raw_event()
+            L.sf_profile_kernel(which, a.cuda_event, b.cuda_event)
+            pairs.append((a, b))
+
+        def disarm():
+            L.sf_profile_kernel(0, None, None)
+
+        blocks = []
+        for i in range(PAIRS):
+            if which in (_lib.KERNEL_CORR_GEMM,):
+                arm()
+            blocks.append(sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4))
+            disarm()
+        group = sfb.CorrGroup(blocks)
+        handle = att(t["inps"])
+        for it in range(ITERS):
+            if which == _lib.KERNEL_LOOKUP:
+                arm()
+            group([t["coords"][it, i] for i in range(PAIRS)])
+            disarm()
+            if which == _lib.KERNEL_GMA_AGGREGATE:
+                arm()
+            agg(handle, t["mfs"])
+            disarm()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) * 1e3 for a, b in pairs]       # microseconds
+
+    kernels = {}
+    if rank == 0:
+        hbm = peaks["hbm_gbs"]
+        us, n = kernel_time(_lib.KERNEL_GMA_AGGREGATE)
+        npad = L.sf_gma_npad(N)
+        bytes_agg = PAIRS * N * npad * 2 + PAIRS * CDIM * npad * 2           # E stream + V, per launch
+        kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / us / 1e3, "peak": hbm, "unit": "GB/s",
+                                    "frac": bytes_agg / us / 1e3 / hbm, "us_per_launch": us, "launches_timed": n,
+                                    "algorithmic_bytes": bytes_agg, "traffic": None,
+                                    "flops": 2.0 * PAIRS * N * N * CDIM}
+        us, n = kernel_time(_lib.KERNEL_LOOKUP)
+        bytes_lk = 2904 * PAIRS * N
+        kernels["corr_lookup"] = {"bound": "hbm", "achieved": bytes_lk / us / 1e3, "peak": hbm, "unit": "GB/s",
+                                  "frac": bytes_lk / us / 1e3 / hbm, "us_per_launch": us, "launches_timed": n,
+                                  "algorithmic_bytes": bytes_lk, "traffic": None,
+                                  "note": "3 pairs per launch, coords random-walk; pyramid 783 MB >> L2"}
+        us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
+        flops = 2.0 * N * N * D
+        tf = flops / us / 1e6
+        peak_tf = peaks["bf16_tflops"]
+        out_bytes = 4 * N * sum((H8 >> l) * (((W8 >> l) + 3) // 4 * 4) for l in range(4))
+        kernels["corr_gemm"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                                "frac": tf / peak_tf, "us_per_launch": us, "launches_timed": n,
+                                "algorithmic_flops": flops, "store_gbs": out_bytes / us / 1e3,
+                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": None,
+                                "note": "fp16 operands (kind::f16), fp32 accumulate; output-store bound"}
+
+    # ---- CPU baseline (rank 0, N=1 only): one full step of the torch CPU port
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import torch_port as tp
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        fm_cpu = host["fm_nhwc"].permute(0, 1, 4, 2, 3)
+        tp.cpu_hot_path(fm_cpu, host["coords"][:2], host["inps"], host["mfs"], host["w_qk"], host["w_v"], host["gamma"])
+        t0 = time.perf_counter()
+        tp.cpu_hot_path(fm_cpu, host["coords"], host["inps"], host["mfs"], host["w_qk"], host["w_v"], host["gamma"])
+        dt = time.perf_counter() - t0
+        cpu = {"value": PAIRS / dt, "unit": "flow frames/s", "cores": cores, "kind": "port",
+               "sample": "1 full step (1 clip: 3 builds + attention + 12 x (3 lookups + aggregate)), fp32 torch CPU"}
+
+    if rank == 0:
+        dom = kernels["gma_aggregate"]
+        line = {
+            "metric": METRIC, "value": world * PAIRS / (ms_step / 1e3), "unit": "flow frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": 1, "pairs": PAIRS, "grid_1_8": [H8, W8], "D": D,
+                       "iters": ITERS, "l2": "inputs larger than L2: the step streams a 783 MB pyramid and "
+                       "297 MB of softmax numerators per rank, no explicit flush", "parallelism": f"clips x{world}"},
+            "e2e": {"value": world * PAIRS / (ms_e2e / 1e3), "unit": "flow frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "peaks": peaks["source"],
+            "corr_lookup_hbm_gbs": kernels["corr_lookup"]["achieved"],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

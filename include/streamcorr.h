@@ -63,6 +63,21 @@ SF_API const char* sf_last_error(void);
 /* 0 if the current device can run the kernels (compute capability 10.x), SF_ERR_NODEVICE otherwise */
 SF_API int sf_device_ok(void);
 
+/* Measurement hooks (used by bench.py; no effect on results).
+ * sf_launch_count: number of kernels this library has launched in the calling thread since load.
+ * sf_profile_kernel: record CUDA events `start` / `stop` (cudaEvent_t as void*) on the call's stream
+ * immediately before / after the NEXT launches of kernel `which`; pass NULL events to stop recording.  */
+#define SF_KERNEL_LOOKUP 1
+#define SF_KERNEL_CORR_GEMM 2
+#define SF_KERNEL_GMA_AGGREGATE 3
+#define SF_KERNEL_GMA_STATS 4
+#define SF_KERNEL_CORR_PACK 5
+#define SF_KERNEL_GMA_PROJ 6
+#define SF_KERNEL_GMA_FINALIZE 7
+#define SF_KERNEL_CORR_SIMT 8
+SF_API int64_t sf_launch_count(void);
+SF_API void sf_profile_kernel(int which, void* start, void* stop);
+
 /* ---- correlation pyramid -------------------------------------------------------------------------
  * Level l of the pyramid is a dense matrix [B*N, h_l * pitch_l] fp32 (N = h*w): row b*N + y*w + x is the
  * h_l x w_l correlation image of query (b,y,x), rows padded to pitch_l = round_up(w_l, 4) floats with

@@ -18,6 +18,18 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local int64_t g_launches = 0;
+static thread_local int g_prof_kind = 0;
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+
+void prof_before(int kind, cudaStream_t s) {
+    ++g_launches;
+    if (kind == g_prof_kind && g_prof_start) cudaEventRecord(g_prof_start, s);
+}
+void prof_after(int kind, cudaStream_t s) {
+    if (kind == g_prof_kind && g_prof_stop) cudaEventRecord(g_prof_stop, s);
+}
+
 LevelGeom make_level_geom(int64_t h, int64_t w) {
     LevelGeom g;
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
@@ -155,6 +167,14 @@ extern "C" {
 int sf_version(void) { return SF_VERSION; }
 
 const char* sf_last_error(void) { return g_err; }
+
+int64_t sf_launch_count(void) { return g_launches; }
+
+void sf_profile_kernel(int which, void* start, void* stop) {
+    g_prof_kind = (start && stop) ? which : 0;
+    g_prof_start = static_cast<cudaEvent_t>(start);
+    g_prof_stop = static_cast<cudaEvent_t>(stop);
+}
 
 int sf_device_ok(void) {
     DeviceInfo di;

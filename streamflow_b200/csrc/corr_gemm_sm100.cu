@@ -236,7 +236,9 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
     }
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
     const int grid = static_cast<int>(std::min<long long>(total, num_sms));
+    prof_before(SF_KERNEL_CORR_GEMM, s);
     corr_gemm_kernel<<<grid, 192, kSmemBytes, s>>>(args);
+    prof_after(SF_KERNEL_CORR_GEMM, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }

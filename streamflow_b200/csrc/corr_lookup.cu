@@ -149,11 +149,13 @@ int launch_corr_lookup(const LookupParams& p, int groups, cudaStream_t s) {
     const long long tiles = (p.BN + kQ - 1) / kQ;
     SF_REQUIRE(tiles > 0 && tiles < (1ll << 31), "corr_lookup: bad query count %lld", p.BN);
     dim3 grid(static_cast<unsigned>(tiles), SF_NUM_LEVELS, static_cast<unsigned>(groups));
+    prof_before(SF_KERNEL_LOOKUP, s);
     if (p.out_f16) {
         corr_lookup_kernel<true><<<grid, 128, 0, s>>>(p);
     } else {
         corr_lookup_kernel<false><<<grid, 128, 0, s>>>(p);
     }
+    prof_after(SF_KERNEL_LOOKUP, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }

@@ -157,15 +157,19 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
     Strided4 t0{f1, s1[0], s1[1], s1[2], s1[3]}, t1{f2, s2[0], s2[1], s2[2], s2[3]};
     const long long per_batch = D * h * w, total = B * per_batch;
     const int blocks = static_cast<int>(std::min<long long>((total + 1023) / 1024, 1184));
+    prof_before(SF_KERNEL_CORR_PACK, s);
     absmax2_kernel<<<dim3(blocks, 2), 256, 0, s>>>(t0, t1, static_cast<int>(D), static_cast<int>(h),
                                                    static_cast<int>(w), per_batch, total, amax_bits);
+    prof_after(SF_KERNEL_CORR_PACK, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
 
 int launch_corr_pack(const PackParams& p, int total_tiles, int64_t B, cudaStream_t s) {
     dim3 grid(total_tiles, (p.D + 63) / 64, static_cast<unsigned>(B));
+    prof_before(SF_KERNEL_CORR_PACK, s);
     corr_pack_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
+    prof_after(SF_KERNEL_CORR_PACK, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }

@@ -98,6 +98,8 @@ int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int
     const LevelGeom g = make_level_geom(h, w);
     const long long N = h * w, total = B * D * N;
     const int gb = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    prof_before(SF_KERNEL_CORR_SIMT, s);
+    prof_before(0, s); prof_before(0, s); prof_before(0, s); prof_before(0, s); prof_before(0, s);   // 6 launches
     gather_dense_kernel<<<gb, 256, 0, s>>>(f1, s1[0], s1[1], s1[2], s1[3], ws_a, (int)D, (int)h, (int)w, total);
     gather_dense_kernel<<<gb, 256, 0, s>>>(f2, s2[0], s2[1], s2[2], s2[3], ws_b, (int)D, (int)h, (int)w, total);
     if (g.pitch[0] != g.w[0])
@@ -111,6 +113,7 @@ int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int
         pool2x2_kernel<<<pb, 256, 0, s>>>(levels[l], levels[l + 1], g.pitch[l], g.img[l], g.h[l + 1], g.w[l + 1],
                                           g.pitch[l + 1], g.img[l + 1], rows);
     }
+    prof_after(SF_KERNEL_CORR_SIMT, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }

@@ -56,6 +56,10 @@ __global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ G
     __half* Xs = reinterpret_cast<__half*>(smem);                    // [C][kXPad]
     __half* Ws = Xs + C * kXPad;                                     // [128][C + 8]
     __half* Ds = Ws + 128 * wpad;                                    // staging, 128 x 72 or 64 x 136
+    // fp32-faithful projection (q, k): x = x_hi + x_lo, w = w_hi + w_lo in fp16, three MMA products
+    const bool faithful = p.split != 0;
+    __half* Xl = Ds + 128 * kXPad;                                   // [C][kXPad]      (faithful only)
+    __half* Wl = Xl + C * kXPad;                                     // [128][C + 8]    (faithful only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * kTok;
@@ -73,11 +77,22 @@ __global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ G
         __half2* d = reinterpret_cast<__half2*>(Xs + c * kXPad + n4);
         d[0] = __floats2half2_rn(v[0], v[1]);
         d[1] = __floats2half2_rn(v[2], v[3]);
+        if (faithful) {
+            const float2 h0 = __half22float2(d[0]), h1 = __half22float2(d[1]);
+            __half2* dl = reinterpret_cast<__half2*>(Xl + c * kXPad + n4);
+            dl[0] = __floats2half2_rn(v[0] - h0.x, v[1] - h0.y);
+            dl[1] = __floats2half2_rn(v[2] - h1.x, v[3] - h1.y);
+        }
     }
     for (int i = tid; i < 128 * (C / 2); i += 256) {
         const int o = i / (C / 2), c2 = (i - o * (C / 2)) * 2;
         const float2 w = *reinterpret_cast<const float2*>(p.w + static_cast<long long>(o) * C + c2);
-        *reinterpret_cast<__half2*>(Ws + o * wpad + c2) = __floats2half2_rn(w.x, w.y);
+        const __half2 wh = __floats2half2_rn(w.x, w.y);
+        *reinterpret_cast<__half2*>(Ws + o * wpad + c2) = wh;
+        if (faithful) {
+            const float2 hf = __half22float2(wh);
+            *reinterpret_cast<__half2*>(Wl + o * wpad + c2) = __floats2half2_rn(w.x - hf.x, w.y - hf.y);
+        }
     }
     __syncthreads();
 
@@ -99,6 +114,26 @@ __global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ G
             ldmatrix_x4_trans(b0, b1, b2, b3, src);
             mma_16816(acc[jt], a, b0, b1);
             mma_16816(acc[jt + 1], a, b2, b3);
+        }
+        if (faithful) {
+            const __half* wlrow = Wl + (warp * 16 + g) * wpad;
+            unsigned al[4];
+            al[0] = *reinterpret_cast<const unsigned*>(wlrow + k0 + 2 * t);
+            al[1] = *reinterpret_cast<const unsigned*>(wlrow + 8 * wpad + k0 + 2 * t);
+            al[2] = *reinterpret_cast<const unsigned*>(wlrow + k0 + 8 + 2 * t);
+            al[3] = *reinterpret_cast<const unsigned*>(wlrow + 8 * wpad + k0 + 8 + 2 * t);
+#pragma unroll
+            for (int jt = 0; jt < 8; jt += 2) {
+                const int mat = lane >> 3, r = lane & 7;
+                const int off = (k0 + (mat & 1) * 8 + r) * kXPad + (jt + (mat >> 1)) * 8;
+                unsigned b0, b1, b2, b3;
+                ldmatrix_x4_trans(b0, b1, b2, b3, Xs + off);      // w_lo * x_hi
+                mma_16816(acc[jt], al, b0, b1);
+                mma_16816(acc[jt + 1], al, b2, b3);
+                ldmatrix_x4_trans(b0, b1, b2, b3, Xl + off);      // w_hi * x_lo
+                mma_16816(acc[jt], a, b0, b1);
+                mma_16816(acc[jt + 1], a, b2, b3);
+            }
         }
     }
 
@@ -153,12 +188,15 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     SF_REQUIRE(p.C % 16 == 0 && p.C >= 16 && p.C <= 256, "gma_proj: C must be a multiple of 16 in [16, 256] (got %d)",
                p.C);
     SF_REQUIRE(p.ld % 8 == 0, "gma_proj: output pitch must be a multiple of 8");
-    const int smem = (p.C * kXPad + 128 * (p.C + 8) + 128 * kXPad) * 2;
+    const int base = (p.C * kXPad + 128 * (p.C + 8)) * 2;
+    const int smem = base + 128 * kXPad * 2 + (p.split ? base : 0);
     const int cols = p.token_major ? p.N : p.ld;
     dim3 grid((cols + kTok - 1) / kTok, p.P);
     auto launch = [&](auto kernel) -> int {
         SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        prof_before(SF_KERNEL_GMA_PROJ, s);
         kernel<<<grid, 256, smem, s>>>(p);
+        prof_after(SF_KERNEL_GMA_PROJ, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;
     };

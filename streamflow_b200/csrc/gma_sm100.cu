@@ -455,7 +455,9 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     SF_CUDA_CHECK(cudaFuncSetAttribute(gma_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kSmemBytes));
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const int grid = static_cast<int>(std::min<long long>(units, num_sms));
+    prof_before(SF_KERNEL_GMA_STATS, s);
     gma_stats_kernel<<<grid, 192, st::kSmemBytes, s>>>(args);
+    prof_after(SF_KERNEL_GMA_STATS, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
@@ -470,26 +472,32 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
         cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ag::kSmemBytes));
     const long long work = static_cast<long long>(p.P) * p.m_tiles * p.k_blocks;
     const int grid = static_cast<int>(std::min<long long>(work, num_sms));
+    prof_before(SF_KERNEL_GMA_AGGREGATE, s);
     gma_aggregate_kernel<<<grid, 192, ag::kSmemBytes, s>>>(args);
+    prof_after(SF_KERNEL_GMA_AGGREGATE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
 
 int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
     dim3 grid((p.N + 31) / 32, p.C / 32, p.P);
+    prof_before(SF_KERNEL_GMA_FINALIZE, s);
     switch (p.fmap_dtype) {
         case SF_DT_F32: gma_finalize_kernel<float><<<grid, dim3(32, 8), 0, s>>>(p); break;
         case SF_DT_F16: gma_finalize_kernel<__half><<<grid, dim3(32, 8), 0, s>>>(p); break;
         case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, s>>>(p); break;
         default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
     }
+    prof_after(SF_KERNEL_GMA_FINALIZE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
 
 int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s) {
     const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 1184));
+    prof_before(0, s);
     fill_u32_kernel<<<blocks, 256, 0, s>>>(ptr, value, n);
+    prof_after(0, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }

@@ -29,6 +29,10 @@ void set_error(const char* fmt, ...);
         }                                \
     } while (0)
 
+// launch accounting + optional event bracketing of one kernel kind (see sf_profile_kernel)
+void prof_before(int kind, cudaStream_t s);
+void prof_after(int kind, cudaStream_t s);
+
 struct LevelGeom {
     int h[SF_NUM_LEVELS], w[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS];
     long long img[SF_NUM_LEVELS];   // floats per query image = h_l * pitch_l
