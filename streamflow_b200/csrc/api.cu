@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sf_internal.h"
@@ -60,6 +61,17 @@ int query_device(DeviceInfo* out) {
         cache.dev = dev;
         cache.sms = sms;
         cache.ok = (major == 10) ? 1 : 0;
+        // The lookup gathers 48-64 B row segments: fetching 32 B sectors instead of the default 64 B pairs on an
+        // L2 miss cuts its DRAM over-fetch (measured with ncu, profiles/).  STREAMCORR_L2_FETCH=0 leaves the
+        // device limit untouched, 64 / 128 select the other granularities.
+        if (cache.ok == 1) {
+            const char* env = getenv("STREAMCORR_L2_FETCH");
+            const int gran = env ? atoi(env) : 32;
+            if (gran == 32 || gran == 64 || gran == 128) {
+                if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(gran)) != cudaSuccess)
+                    cudaGetLastError();
+            }
+        }
     }
     if (cache.ok != 1) {
         set_error("device %d is not sm_100 (Blackwell B200): kernels are built for sm_100a only, no fallback", dev);

@@ -9,11 +9,11 @@
 // TMA stores of tile i overlap the MMAs of tile i+1.
 //
 // CTA = 192 threads, 1 CTA / SM, persistent over a contiguous range of (batch, m-tile, n-tile) tiles:
-//   warp 0      TMA producer: A (128 x 64) and B (256 x 64) fp16 k-blocks, 128B swizzle, 4-stage mbarrier ring
+//   warp 0      TMA producer: A (128 x 64) and B (256 x 64) fp16 k-blocks, 128B swizzle, 3-stage mbarrier ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16, kind::f16, fp32 accum),
 //               two 256-column accumulators in TMEM (double buffered against the epilogue)
 //   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale -> swizzled smem -> TMA store (3-D map,
-//               clips ragged edges), two 4 KB staging buffers per warp
+//               clips ragged edges), four 4 KB staging buffers per warp = 64 KB of stores in flight per SM
 #include "sf_internal.h"
 #include "sm100_ptx.cuh"
 
@@ -22,12 +22,13 @@ namespace sf {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
+constexpr int kEpiBufs = 4;                           // staging buffers (TMA stores in flight) per epilogue warp
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiBuf = 32 * 32 * 4;                 // 32 rows x 128 B
-constexpr int kEpiBytes = 4 * 2 * kEpiBuf;
+constexpr int kEpiBytes = 4 * kEpiBufs * kEpiBuf;
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;
 
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
     } else {
         const int e = warp - 2;            // staging buffers of this warp
         const int quad = warp & 3;         // TMEM lane quadrant this warp may read
-        uint8_t* bufs = epi_base + e * 2 * kEpiBuf;
+        uint8_t* bufs = epi_base + e * kEpiBufs * kEpiBuf;
         const int e1 = scale_exponent_from_bits(p.amax_bits[0]);
         const int e2 = scale_exponent_from_bits(p.amax_bits[1]);
         const float alpha = p.inv_sqrt_d * exp2f(static_cast<float>(-(e1 + e2)));
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
                 const int col0 = c.ntl * BN + ch * 32;
                 if (col0 >= ncols || row0 >= p.N) continue;          // warp-uniform
                 uint8_t* buf = bufs + buf_sel * kEpiBuf;
-                if (lane == 0) tma_store_wait_read<1>();              // the store that last read `buf` is done
+                if (lane == 0) tma_store_wait_read<kEpiBufs - 1>();   // the store that last read `buf` is done
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
                     tma_store_3d(&args.tm_out[c.level], buf, col0, row0, c.b);
                     tma_store_commit();
                 }
-                buf_sel ^= 1;
+                buf_sel = (buf_sel + 1) % kEpiBufs;
             }
         }
         if (lane == 0) tma_store_wait_all<0>();

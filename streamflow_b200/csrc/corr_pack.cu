@@ -8,6 +8,9 @@
 //                   the volume uses linearity: avg_pool(f1^T f2) == f1^T avg_pool(f2) (core/corr.py:19-21).
 //                   With split != 0 each value is stored as hi/lo fp16 parts concatenated along K so that one
 //                   GEMM over Kp = 3*D accumulates  hi*hi + hi*lo + lo*hi  (fp32-faithful mode).
+#include <algorithm>
+#include <utility>
+
 #include "sf_internal.h"
 
 namespace sf {
@@ -46,6 +49,26 @@ __global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, lo
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+}
+
+// dense per-batch blocks (NCHW-contiguous or channels-last): plain vectorised sweep of the storage
+__global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long sb0, long long sb1, int B,
+                                    long long per_batch, unsigned* out_bits) {
+    const float* f = blockIdx.y == 0 ? f0 : f1;
+    const long long sb = blockIdx.y == 0 ? sb0 : sb1;
+    const long long n4 = per_batch >> 2;
+    float m = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float4* v = reinterpret_cast<const float4*>(f + b * sb);
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const float4 q = __ldg(v + i);
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
 }
 
 __device__ __forceinline__ float src_at(const PackSeg& s, long long boff, int k, int y, int x) {
@@ -93,6 +116,8 @@ __device__ float pooled_at(const PackSeg& s, long long boff, int k, int v, int u
 // CTA = 32 rows x 64 channels of one segment / batch element.  blockDim = (32, 8).
 __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ PackParams p) {
     __shared__ float tile[64][33];
+    __shared__ int s_v[32], s_u[32];
+    __shared__ float s_scale;
 
     int si = 0;
 #pragma unroll
@@ -103,9 +128,17 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     const int k0 = blockIdx.y * 64;
     const int b = blockIdx.z;
     const long long boff = b * s.sb;
-    const float scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[s.amax_slot])));
     const int tx = threadIdx.x, ty = threadIdx.y;
     const bool kfast = (s.sk == 1);
+    if (ty == 0) {      // one division per row and ONE read of the scale word per CTA (no same-address hot spot)
+        const int m = row0 + tx;
+        const int v = m / s.pitch;
+        s_v[tx] = v;
+        s_u[tx] = m - v * s.pitch;
+        if (tx == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[s.amax_slot])));
+    }
+    __syncthreads();
+    const float scale = s_scale;
 
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -120,7 +153,7 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
         const int m = row0 + rr;
         float val = 0.f;
         if (m < s.rows && k0 + kk < p.D) {
-            const int v = m / s.pitch, u = m - v * s.pitch;
+            const int v = s_v[rr], u = s_u[rr];
             if (u < s.wl) val = pooled_at(s, boff, k0 + kk, v, u) * scale;
         }
         tile[kk][rr] = val;
@@ -156,6 +189,23 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
     SF_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 2 * sizeof(unsigned), s));
     Strided4 t0{f1, s1[0], s1[1], s1[2], s1[3]}, t1{f2, s2[0], s2[1], s2[2], s2[3]};
     const long long per_batch = D * h * w, total = B * per_batch;
+    auto dense = [&](const int64_t st[4]) {
+        int64_t sz[3] = {D, h, w}, sd[3] = {st[1], st[2], st[3]};
+        for (int i = 0; i < 3; ++i)
+            for (int j = i + 1; j < 3; ++j)
+                if (sd[j] < sd[i]) { std::swap(sd[i], sd[j]); std::swap(sz[i], sz[j]); }
+        return sd[0] == 1 && sd[1] == sz[0] && sd[2] == sz[0] * sz[1];
+    };
+    if (dense(s1) && dense(s2) && per_batch % 4 == 0 && s1[0] % 4 == 0 && s2[0] % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0) {
+        const int fb = static_cast<int>(std::min<long long>((per_batch / 4 + 255) / 256, 592));
+        prof_before(SF_KERNEL_CORR_PACK, s);
+        absmax2_flat_kernel<<<dim3(fb, 2), 256, 0, s>>>(f1, f2, s1[0], s2[0], static_cast<int>(B), per_batch,
+                                                        amax_bits);
+        prof_after(SF_KERNEL_CORR_PACK, s);
+        SF_CUDA_CHECK(cudaGetLastError());
+        return SF_OK;
+    }
     const int blocks = static_cast<int>(std::min<long long>((total + 1023) / 1024, 1184));
     prof_before(SF_KERNEL_CORR_PACK, s);
     absmax2_kernel<<<dim3(blocks, 2), 256, 0, s>>>(t0, t1, static_cast<int>(D), static_cast<int>(h),

@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, v_off, acc_off, total;
+    int64_t q_off, k_off, rowmax_off, v_off, acc_off, rscale_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -20,6 +20,7 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
     ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
     ws.acc_off = off;     off += align_up(P * N * d * 4, 1024);
+    ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
     ws.total = off;
     return ws;
 }
@@ -128,6 +129,7 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     pv.scale = 1.0f;
     pv.out = reinterpret_cast<__half*>(wsb + ws.v_off);
     pv.out_batch_stride = d * Npad; pv.ld = (int)Npad; pv.token_major = 0; pv.split = 0; pv.is_b = 0;
+    pv.rowsum = rowsum; pv.gamma = gamma; pv.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
     if (int rc = launch_gma_proj(pv, s)) return rc;
 
     CUtensorMap tm_e, tm_v;
@@ -143,9 +145,8 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     ap.m_tiles = (int)((N + 127) / 128);
     ap.k_blocks = (int)(Npad / 64);
     ap.acc = reinterpret_cast<float*>(wsb + ws.acc_off);
-    ap.rowsum = rowsum;
+    ap.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
     ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
-    ap.gamma = gamma;
     ap.out = out;
     if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
     return launch_gma_finalize(ap, s);

@@ -49,7 +49,7 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const unsigned (&a)[4],
 // CTA: 256 threads = 8 warps; tile = 128 outputs x 64 tokens; warp w owns outputs [16w, 16w+16).
 // Requires O == 128 per launch (rows o0..o0+127 of W), C % 16 == 0, C <= 256.
 template <typename T>
-__global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ GmaProjParams p) {
+__global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant__ GmaProjParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int C = p.C;
     const int wpad = C + 8;
@@ -66,32 +66,72 @@ __global__ void __launch_bounds__(256) gma_proj_kernel(const __grid_constant__ G
     const int pb = blockIdx.y;
     const T* X = reinterpret_cast<const T*>(p.x) + static_cast<long long>(pb) * C * p.N;
 
-    for (int i = tid; i < C * (kTok / 4); i += 256) {
-        const int c = i / (kTok / 4), n4 = (i - c * (kTok / 4)) * 4;
-        float v[4];
+    if (p.rscale != nullptr && tid < kTok && n0 + tid < p.N) {
+        const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
+        p.rscale[r] = __ldg(p.gamma) / __ldg(p.rowsum + r);
+    }
+    // X tile [C][64 tokens]: all global loads of a batch are issued before any conversion so they overlap
+    const bool vec_ok = (sizeof(T) == 4) && ((p.N & 3) == 0) && (n0 + kTok <= p.N) &&
+                        ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    for (int i0 = tid; i0 < C * (kTok / 4); i0 += 256 * 8) {
+        float v[8][4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int n = n0 + n4 + e;
-            v[e] = (n < p.N) ? load_as_float<T>(X + static_cast<long long>(c) * p.N + n) : 0.f;
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            const int c = i / (kTok / 4), n4 = (i - c * (kTok / 4)) * 4;
+            if (i < C * (kTok / 4)) {
+                if (vec_ok) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(
+                        reinterpret_cast<const float*>(X) + static_cast<long long>(c) * p.N + n0 + n4));
+                    v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int n = n0 + n4 + e;
+                        v[u][e] = (n < p.N) ? load_as_float<T>(X + static_cast<long long>(c) * p.N + n) : 0.f;
+                    }
+                }
+            }
         }
-        __half2* d = reinterpret_cast<__half2*>(Xs + c * kXPad + n4);
-        d[0] = __floats2half2_rn(v[0], v[1]);
-        d[1] = __floats2half2_rn(v[2], v[3]);
-        if (faithful) {
-            const float2 h0 = __half22float2(d[0]), h1 = __half22float2(d[1]);
-            __half2* dl = reinterpret_cast<__half2*>(Xl + c * kXPad + n4);
-            dl[0] = __floats2half2_rn(v[0] - h0.x, v[1] - h0.y);
-            dl[1] = __floats2half2_rn(v[2] - h1.x, v[3] - h1.y);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i >= C * (kTok / 4)) continue;
+            const int c = i / (kTok / 4), n4 = (i - c * (kTok / 4)) * 4;
+            __half2* d = reinterpret_cast<__half2*>(Xs + c * kXPad + n4);
+            d[0] = __floats2half2_rn(v[u][0], v[u][1]);
+            d[1] = __floats2half2_rn(v[u][2], v[u][3]);
+            if (faithful) {
+                const float2 h0 = __half22float2(d[0]), h1 = __half22float2(d[1]);
+                __half2* dl = reinterpret_cast<__half2*>(Xl + c * kXPad + n4);
+                dl[0] = __floats2half2_rn(v[u][0] - h0.x, v[u][1] - h0.y);
+                dl[1] = __floats2half2_rn(v[u][2] - h1.x, v[u][3] - h1.y);
+            }
         }
     }
-    for (int i = tid; i < 128 * (C / 2); i += 256) {
-        const int o = i / (C / 2), c2 = (i - o * (C / 2)) * 2;
-        const float2 w = *reinterpret_cast<const float2*>(p.w + static_cast<long long>(o) * C + c2);
-        const __half2 wh = __floats2half2_rn(w.x, w.y);
-        *reinterpret_cast<__half2*>(Ws + o * wpad + c2) = wh;
-        if (faithful) {
-            const float2 hf = __half22float2(wh);
-            *reinterpret_cast<__half2*>(Wl + o * wpad + c2) = __floats2half2_rn(w.x - hf.x, w.y - hf.y);
+    // W [128][C] fp32 -> fp16 (C % 16 == 0, rows 16-byte aligned)
+    for (int i0 = tid; i0 < 128 * (C / 4); i0 += 256 * 8) {
+        float4 wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i < 128 * (C / 4)) wv[u] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 256;
+            if (i >= 128 * (C / 4)) continue;
+            const int o = i / (C / 4), c4 = (i - o * (C / 4)) * 4;
+            const __half2 w0 = __floats2half2_rn(wv[u].x, wv[u].y), w1 = __floats2half2_rn(wv[u].z, wv[u].w);
+            __half2* d = reinterpret_cast<__half2*>(Ws + o * wpad + c4);
+            d[0] = w0;
+            d[1] = w1;
+            if (faithful) {
+                const float2 f0 = __half22float2(w0), f1 = __half22float2(w1);
+                __half2* dl = reinterpret_cast<__half2*>(Wl + o * wpad + c4);
+                dl[0] = __floats2half2_rn(wv[u].x - f0.x, wv[u].y - f0.y);
+                dl[1] = __floats2half2_rn(wv[u].z - f1.x, wv[u].w - f1.y);
+            }
         }
     }
     __syncthreads();
@@ -188,6 +228,7 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     SF_REQUIRE(p.C % 16 == 0 && p.C >= 16 && p.C <= 256, "gma_proj: C must be a multiple of 16 in [16, 256] (got %d)",
                p.C);
     SF_REQUIRE(p.ld % 8 == 0, "gma_proj: output pitch must be a multiple of 8");
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "gma_proj: weight pointer must be 16-byte aligned");
     const int base = (p.C * kXPad + 128 * (p.C + 8)) * 2;
     const int smem = base + 128 * kXPad * 2 + (p.split ? base : 0);
     const int cols = p.token_major ? p.N : p.ld;

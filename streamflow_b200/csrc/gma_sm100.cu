@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
 
     const GmaStatsParams& p = args.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = (p.Kp + BK - 1) / BK;
+    // pass 1 only needs an approximate row max (any m within a few units of the true max keeps exp() in range and
+    // cancels in E / rowsum): use the hi parts alone (first d columns); pass 2 uses the full hi/lo-split K
+    const int kblocks = (p.pass == 1 ? (p.Kp / 3 + BK - 1) / BK : (p.Kp + BK - 1) / BK);
     const int per_chunk = (p.n_tiles + p.chunks - 1) / p.chunks;
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const long long u_begin = units * blockIdx.x / gridDim.x;
@@ -256,10 +258,13 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
 // =====================================================================================================
 namespace ag {
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
-constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+// E (the HBM stream) and V (L2 resident) ride separate mbarrier rings: HBM latency x 44 GB/s/SM needs ~90 KB
+// in flight per SM, so the E ring is deep and the V ring shallow.
+constexpr int kEStages = 9, kVStages = 4;
+constexpr int kTileBytes = BM * BK * 2;                  // 16 KB (E tile and V tile have the same size)
+constexpr int kSmemBytes = (kEStages + kVStages) * kTileBytes + 1024 + 512;
 constexpr int kTmemCols = 256;
+constexpr int kThreads = 224;                            // warps: 0 E-producer, 1 MMA, 2 V-producer, 3-6 epilogue
 }  // namespace ag
 
 struct GmaAggArgs {
@@ -267,17 +272,20 @@ struct GmaAggArgs {
     GmaAggParams p;
 };
 
-__global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
+__global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
     using namespace ag;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + kStages;
-    uint64_t* tfull = bars + 2 * kStages;
-    uint64_t* tempty = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint8_t* e_base = smem;
+    uint8_t* v_base = smem + kEStages * kTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kEStages + kVStages) * kTileBytes);
+    uint64_t* e_full = bars;
+    uint64_t* e_empty = e_full + kEStages;
+    uint64_t* v_full = e_empty + kEStages;
+    uint64_t* v_empty = v_full + kVStages;
+    uint64_t* tfull = v_empty + kVStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const GmaAggParams& p = args.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,9 +297,13 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.tm_e);
         tma_prefetch_desc(&args.tm_v);
-        for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+        for (int i = 0; i < kEStages; ++i) {
+            mbar_init(&e_full[i], 1);
+            mbar_init(&e_empty[i], 1);
+        }
+        for (int i = 0; i < kVStages; ++i) {
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -305,8 +317,13 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 2) {
         if (lane == 0) {
+            const bool is_e = (warp == 0);
+            const int nst = is_e ? kEStages : kVStages;
+            uint64_t* fullb = is_e ? e_full : v_full;
+            uint64_t* emptyb = is_e ? e_empty : v_empty;
+            uint8_t* base = is_e ? e_base : v_base;
             int stage = 0;
             uint32_t phase = 0;
             for (long long pos = w_begin; pos < w_end; ++pos) {
@@ -314,12 +331,15 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
                 const int kb = static_cast<int>(pos - tile * KB);
                 const int pb = static_cast<int>(tile / p.m_tiles);
                 const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* sa = stage_base + stage * kStageBytes;
-                mbar_expect_tx(&full[stage], kStageBytes);
-                tma_load_3d_hint(&args.tm_e, &full[stage], sa, kb * BK, mt * BM, pb, kEvictFirst);
-                tma_load_3d_hint(&args.tm_v, &full[stage], sa + kABytes, kb * BK, 0, pb, kEvictLast);
-                if (++stage == kStages) {
+                mbar_wait(&emptyb[stage], phase ^ 1);
+                mbar_expect_tx(&fullb[stage], kTileBytes);
+                if (is_e)
+                    tma_load_3d_hint(&args.tm_e, &fullb[stage], base + stage * kTileBytes, kb * BK, mt * BM, pb,
+                                     kEvictFirst);
+                else
+                    tma_load_3d_hint(&args.tm_v, &fullb[stage], base + stage * kTileBytes, kb * BK, 0, pb,
+                                     kEvictLast);
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -328,8 +348,8 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
-            int stage = 0, local = 0;
-            uint32_t phase = 0;
+            int es = 0, vs = 0, local = 0;
+            uint32_t ephase = 0, vphase = 0;
             long long pos = w_begin;
             while (pos < w_end) {
                 const long long tile = pos / KB;
@@ -340,18 +360,24 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 bool first = true;
                 for (; pos < seg_end; ++pos) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&v_full[vs], vphase);
+                    mbar_wait(&e_full[es], ephase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-                    const uint64_t da = make_kmajor_sw128_desc(sa);
-                    const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(e_base + es * kTileBytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(v_base + vs * kTileBytes));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                     first = false;
-                    umma_commit(&empty[stage]);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
+                    umma_commit(&e_empty[es]);
+                    umma_commit(&v_empty[vs]);
+                    if (++es == kEStages) {
+                        es = 0;
+                        ephase ^= 1;
+                    }
+                    if (++vs == kVStages) {
+                        vs = 0;
+                        vphase ^= 1;
                     }
                 }
                 umma_commit(&tfull[acc]);
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(192, 1) gma_aggregate_kernel(const __grid_cons
     }
 }
 
-// out[p, c, n] = fmap[p, c, n] + gamma * acc[p, n, c] / rowsum[p, n];  acc <- 0.   block (32, 8)
+// out[p, c, n] = fmap[p, c, n] + acc[p, n, c] * (gamma / rowsum[p, n]);  acc <- 0.   block (32, 8)
 template <typename T>
 __global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
     __shared__ float tile[32][33];
@@ -423,17 +449,16 @@ __global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant
         tile[ty + 8 * i][tx] = v;
     }
     __syncthreads();
-    const float gamma = __ldg(p.gamma);
     const int n = n0 + tx;
     if (n >= p.N) return;
-    const float rinv = 1.0f / __ldg(p.rowsum + static_cast<long long>(pb) * p.N + n);
+    const float rs = __ldg(p.rscale + static_cast<long long>(pb) * p.N + n);      // gamma / rowsum
     const T* fm = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(pb) * p.C * p.N;
     float* out = p.out + static_cast<long long>(pb) * p.C * p.N;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = c0 + ty + 8 * i;
         const long long idx = static_cast<long long>(c) * p.N + n;
-        out[idx] = static_cast<float>(fm[idx]) + gamma * (tile[tx][ty + 8 * i] * rinv);
+        out[idx] = fmaf(tile[tx][ty + 8 * i], rs, static_cast<float>(fm[idx]));
     }
 }
 
@@ -473,7 +498,7 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
     const long long work = static_cast<long long>(p.P) * p.m_tiles * p.k_blocks;
     const int grid = static_cast<int>(std::min<long long>(work, num_sms));
     prof_before(SF_KERNEL_GMA_AGGREGATE, s);
-    gma_aggregate_kernel<<<grid, 192, ag::kSmemBytes, s>>>(args);
+    gma_aggregate_kernel<<<grid, ag::kThreads, ag::kSmemBytes, s>>>(args);
     prof_after(SF_KERNEL_GMA_AGGREGATE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

@@ -126,6 +126,11 @@ struct GmaProjParams {
     int token_major;
     int split;            // token-major only: also write lo/hi split parts at column offsets O and 2*O
     int is_b;
+    // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the finalize kernel,
+    // so that no later kernel has thousands of warps reading the single gamma word
+    const float* rowsum;
+    const float* gamma;
+    float* rscale;
 };
 int launch_gma_proj(const GmaProjParams& p, cudaStream_t s);
 
@@ -145,10 +150,9 @@ struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
     int m_tiles, k_blocks;      // ceil(N/128), Npad/64
     float* acc;                 // [P, N, 128] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
-    const float* rowsum;        // [P, N]
+    const float* rscale;        // [P, N] gamma / rowsum (written by the v projection)
     const void* fmap;           // [P, C, N]
     int fmap_dtype;
-    const float* gamma;
     float* out;                 // [P, C, N]
 };
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
