@@ -260,18 +260,21 @@ def run_ours(args):
 
         blocks = []
         for i in range(PAIRS):
-            if which in (_lib.KERNEL_CORR_GEMM,):
+            if which in (_lib.KERNEL_CORR_GEMM, _lib.KERNEL_CORR_PACK):
                 arm()
             blocks.append(sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4))
             disarm()
         group = sfb.CorrGroup(blocks)
+        if which == _lib.KERNEL_GMA_STATS:
+            arm()
         handle = att(t["inps"])
+        disarm()
         for it in range(ITERS):
             if which == _lib.KERNEL_LOOKUP:
                 arm()
             group([t["coords"][it, i] for i in range(PAIRS)])
             disarm()
-            if which == _lib.KERNEL_GMA_AGGREGATE:
+            if which in (_lib.KERNEL_GMA_AGGREGATE, _lib.KERNEL_GMA_PROJ, _lib.KERNEL_GMA_FINALIZE):
                 arm()
             agg(handle, t["mfs"])
             disarm()
@@ -304,6 +307,13 @@ def run_ours(args):
                                 "algorithmic_flops": flops, "store_gbs": out_bytes / us / 1e3,
                                 "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": None,
                                 "note": "fp16 operands (kind::f16), fp32 accumulate; output-store bound"}
+
+        # the small helper kernels, for the step budget in DESIGN.md (event pair brackets the last launch of the
+        # kind inside each public call)
+        for name, kind in (("gma_proj_v", _lib.KERNEL_GMA_PROJ), ("gma_finalize", _lib.KERNEL_GMA_FINALIZE),
+                           ("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
+            us, n = kernel_time(kind)
+            kernels[name] = {"us_per_launch": us, "launches_timed": n}
 
     # ---- CPU baseline (rank 0, N=1 only): one full step of the torch CPU port
     cpu = None

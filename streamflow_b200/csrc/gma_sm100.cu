@@ -11,7 +11,7 @@
 //   gma_aggregate_kernel  stream-K partition of all (map, query-tile, key-block) work over the SMs so every SM
 //                         streams the same number of bytes; partial 128 x 128 tiles are reduced with vector
 //                         red.global.add into an fp32 buffer.
-//   gma_finalize_kernel   out = fmap + gamma * acc / rowsum  (transposing [N, C] -> NCHW) and re-zeroes acc.
+//   gma_finalize_kernel   out = fmap + acc * (gamma / rowsum) on the channel-major accumulator, and re-zeroes acc.
 #include <cuda_bf16.h>
 
 #include "sf_internal.h"
@@ -397,7 +397,9 @@ __global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __
             mbar_wait(&tfull[acc], (local >> 1) & 1);
             tc_fence_after();
             const int row = mt * BM + quad * 32 + lane;
-            float* dst = p.acc + (static_cast<long long>(pb) * p.N + row) * BN;
+            // acc is channel-major [P, 128, N] (the layout of the NCHW result): for a fixed channel the 32 lanes
+            // of a warp hit 32 consecutive floats, so every warp-level red is one fully coalesced 128 B line
+            float* dst = p.acc + static_cast<long long>(pb) * BN * p.N + row;
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t v[32];
@@ -410,10 +412,9 @@ __global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __
                 }
                 if (row < p.N) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + ch * 32 + 4 * j),
-                                     "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                                     "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                    for (int j = 0; j < 32; ++j)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(ch * 32 + j) * p.N),
+                                     "f"(__uint_as_float(v[j]))
                                      : "memory");
                 }
             }
@@ -430,35 +431,39 @@ __global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __
     }
 }
 
-// out[p, c, n] = fmap[p, c, n] + acc[p, n, c] * (gamma / rowsum[p, n]);  acc <- 0.   block (32, 8)
+// out[p, c, n] = fmap[p, c, n] + acc[p, c, n] * (gamma / rowsum[p, n]);  acc <- 0.   Pure streaming, 4 floats/thread.
 template <typename T>
 __global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
-    __shared__ float tile[32][33];
-    const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32, pb = blockIdx.z;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    float* acc = p.acc + static_cast<long long>(pb) * p.N * 128;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + ty + 8 * i;
-        float v = 0.f;
-        if (n < p.N) {
-            float* a = acc + static_cast<long long>(n) * 128 + c0 + tx;
-            v = *a;
-            *a = 0.f;
+    const long long per_map = static_cast<long long>(p.C) * p.N;
+    const long long total = static_cast<long long>(p.P) * per_map;
+    const T* fm = reinterpret_cast<const T*>(p.fmap);
+    if ((p.N & 3) == 0) {
+        const long long total4 = total >> 2;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+             i += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const long long e = i << 2;
+            const long long pb = e / per_map;
+            const int n = static_cast<int>((e - pb * per_map) % p.N);
+            float4* ap = reinterpret_cast<float4*>(p.acc + e);
+            const float4 a = *ap;
+            *ap = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale + pb * p.N + n));
+            float4 o;
+            o.x = fmaf(a.x, rs.x, static_cast<float>(fm[e + 0]));
+            o.y = fmaf(a.y, rs.y, static_cast<float>(fm[e + 1]));
+            o.z = fmaf(a.z, rs.z, static_cast<float>(fm[e + 2]));
+            o.w = fmaf(a.w, rs.w, static_cast<float>(fm[e + 3]));
+            __stcs(reinterpret_cast<float4*>(p.out + e), o);
         }
-        tile[ty + 8 * i][tx] = v;
-    }
-    __syncthreads();
-    const int n = n0 + tx;
-    if (n >= p.N) return;
-    const float rs = __ldg(p.rscale + static_cast<long long>(pb) * p.N + n);      // gamma / rowsum
-    const T* fm = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(pb) * p.C * p.N;
-    float* out = p.out + static_cast<long long>(pb) * p.C * p.N;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i;
-        const long long idx = static_cast<long long>(c) * p.N + n;
-        out[idx] = fmaf(tile[tx][ty + 8 * i], rs, static_cast<float>(fm[idx]));
+    } else {
+        for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
+             e += static_cast<long long>(gridDim.x) * blockDim.x) {
+            const long long pb = e / per_map;
+            const int n = static_cast<int>((e - pb * per_map) % p.N);
+            const float a = p.acc[e];
+            p.acc[e] = 0.f;
+            p.out[e] = fmaf(a, __ldg(p.rscale + pb * p.N + n), static_cast<float>(fm[e]));
+        }
     }
 }
 
@@ -505,12 +510,13 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
 }
 
 int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
-    dim3 grid((p.N + 31) / 32, p.C / 32, p.P);
+    const long long total = static_cast<long long>(p.P) * p.C * p.N;
+    const int grid = static_cast<int>(std::min<long long>((total / 4 + 255) / 256, 148 * 8));
     prof_before(SF_KERNEL_GMA_FINALIZE, s);
     switch (p.fmap_dtype) {
-        case SF_DT_F32: gma_finalize_kernel<float><<<grid, dim3(32, 8), 0, s>>>(p); break;
-        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, dim3(32, 8), 0, s>>>(p); break;
-        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, s>>>(p); break;
+        case SF_DT_F32: gma_finalize_kernel<float><<<grid, 256, 0, s>>>(p); break;
+        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, 256, 0, s>>>(p); break;
+        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
         default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
     }
     prof_after(SF_KERNEL_GMA_FINALIZE, s);

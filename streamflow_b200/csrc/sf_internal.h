@@ -149,7 +149,7 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
     int m_tiles, k_blocks;      // ceil(N/128), Npad/64
-    float* acc;                 // [P, N, 128] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
+    float* acc;                 // [P, 128, N] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
     const float* rscale;        // [P, N] gamma / rowsum (written by the v projection)
     const void* fmap;           // [P, C, N]
     int fmap_dtype;
