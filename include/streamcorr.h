@@ -109,12 +109,15 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
  * Q and K are constant over the refinement iterations, so sf_gma_attention computes ONCE per clip
  *     E[p,i,j]   = fp16(2^12 * exp(s_ij - max_j s_ij)),   s = (scale * q) . k,   [q; k] = W_qk . fmap
  *     rowsum[p,i] = sum_j E[p,i,j]                         (softmax = E / rowsum)
- * with E stored as [P, N, Npad] fp16 (Npad = sf_gma_npad(N) = round_up(N, 64), pad columns zero), and
+ * with E stored tile-major as [P][ceil(N/128)][Npad/64][128][64] fp16 (Npad = sf_gma_npad(N) = round_up(N, 64);
+ * every 128-query x 64-key tile is one contiguous 16 KB block so the per-iteration stream reads whole DRAM
+ * pages; pad key columns are zero; sf_gma_e_elems(P, N) is the element count to allocate), and
  * sf_gma_aggregate computes every iteration
  *     out = fmap + gamma * ((E / rowsum) . (W_v . fmap)^T).
  * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) must be the SAME buffer for the attention call
  * and all aggregate calls that use its E: it holds the fp32 accumulation buffer the aggregate keeps zeroed. */
 SF_API int64_t sf_gma_npad(int64_t N);
+SF_API int64_t sf_gma_e_elems(int64_t P, int64_t N);
 SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);
 
 /* fmap: [P, C, N] (NCHW flattened, contiguous) of dtype fmap_dtype; w_qk: [2*d, C] fp32 contiguous

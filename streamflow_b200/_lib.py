@@ -25,7 +25,8 @@ KERNEL_CORR_PACK, KERNEL_GMA_PROJ, KERNEL_GMA_FINALIZE, KERNEL_CORR_SIMT = 5, 6,
 
 EXPORTS = [
     "sf_version", "sf_last_error", "sf_device_ok", "sf_launch_count", "sf_profile_kernel", "sf_corr_level_dims", "sf_corr_workspace_bytes",
-    "sf_corr_build", "sf_corr_lookup", "sf_corr_lookup_group", "sf_gma_npad", "sf_gma_workspace_bytes",
+    "sf_corr_build", "sf_corr_lookup", "sf_corr_lookup_group", "sf_gma_npad", "sf_gma_e_elems",
+    "sf_gma_workspace_bytes",
     "sf_gma_attention", "sf_gma_aggregate",
 ]
 
@@ -67,6 +68,8 @@ def lib() -> ctypes.CDLL:
     L.sf_corr_lookup_group.restype = c_int
     L.sf_gma_npad.argtypes = [c_int64]
     L.sf_gma_npad.restype = c_int64
+    L.sf_gma_e_elems.argtypes = [c_int64, c_int64]
+    L.sf_gma_e_elems.restype = c_int64
     L.sf_gma_workspace_bytes.argtypes = [c_int64, c_int64, c_int64, c_int64]
     L.sf_gma_workspace_bytes.restype = c_int64
     L.sf_gma_attention.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,

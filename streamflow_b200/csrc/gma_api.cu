@@ -49,6 +49,8 @@ extern "C" {
 
 int64_t sf_gma_npad(int64_t N) { return align_up(N, 64); }
 
+int64_t sf_gma_e_elems(int64_t P, int64_t N) { return P * align_up(N, 128) * align_up(N, 64); }
+
 int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d) {
     (void)C;
     if (P < 1 || N < 1 || d < 1) return 0;
@@ -91,7 +93,9 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     if (int rc = make_tmap3(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.k_off, kp, N, P, kp * 2, N * kp * 2, 64,
                             256, "K"))
         return rc;
-    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, Npad, N, P, Npad * 2, N * Npad * 2, 64, 32,
+    // E is tile-major [P][m_tiles][Npad/64][128][64]: a 2-D view of 128-byte rows per map
+    const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
+    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 32,
                             "E(store)"))
         return rc;
 
@@ -133,7 +137,8 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     if (int rc = launch_gma_proj(pv, s)) return rc;
 
     CUtensorMap tm_e, tm_v;
-    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, Npad, N, P, Npad * 2, N * Npad * 2, 64, 128,
+    const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
+    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 128,
                             "E(load)"))
         return rc;
     if (int rc = make_tmap3(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.v_off, Npad, d, P, Npad * 2,

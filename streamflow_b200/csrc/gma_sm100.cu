@@ -2,7 +2,7 @@
 // tcgen05 tensor cores.
 //
 // Q and K do not change across refinement iterations, so the softmax numerator is computed ONCE per clip and
-// kept in HBM as fp16 (E = 2^12 * exp(s - rowmax), [P, N, Npad], 99 MB per Sintel map -- trivial against 180 GB),
+// kept in HBM as fp16 (E = 2^12 * exp(s - rowmax), tile-major 16 KB blocks, 99 MB per Sintel map -- trivial against 180 GB),
 // exactly the matrix the reference's autocast path re-casts to fp16 every iteration (core/gma.py:95-97).
 // Every iteration is then one streaming GEMM  acc = E . V^T  bound by reading E from HBM:
 //
@@ -37,12 +37,14 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 // =====================================================================================================
 namespace st {
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quadrant, 128 columns each
 constexpr int kEpiBuf = 32 * 128;                       // 32 rows x 64 fp16
-constexpr int kEpiBytes = 4 * 2 * kEpiBuf;
+constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBuf;
 constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
 constexpr int kTmemCols = 512;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 }  // namespace st
 
 struct GmaStatsArgs {
@@ -50,7 +52,7 @@ struct GmaStatsArgs {
     GmaStatsParams p;
 };
 
-__global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
+__global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
     using namespace st;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], kEpiWarps);
         }
         fence_mbar_init();
     }
@@ -157,8 +159,9 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
             }
         }
     } else {
-        const int e = warp - 2, quad = warp & 3;
+        const int e = warp - 2, quad = warp & 3, half = e >> 2;     // half: which 128 of the 256 key columns
         uint8_t* bufs = epi_base + e * 2 * kEpiBuf;
+        const int kbk = p.Npad / 64;                                // 64-key blocks per row of E
         int local = 0, buf_sel = 0;
         for (long long u = u_begin; u < u_end; ++u) {
             int pb, mt, nt0, nt1;
@@ -173,48 +176,65 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
                 mbar_wait(&tfull[acc], (local >> 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int cp = 0; cp < BN / 64; ++cp) {      // pairs of 32-column chunks = 64 keys
+                for (int cq = 0; cq < 2; ++cq) {            // this warp's two 64-key column groups
+                    const int cp = half * 2 + cq;
                     uint32_t v0[32], v1[32];
                     const uint32_t taddr =
                         tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cp * 64;
                     tmem_ld_32x32(taddr, v0);
                     tmem_ld_32x32(taddr + 32, v1);
                     tmem_ld_wait();
-                    if (cp == BN / 64 - 1) {
+                    if (cq == 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
                     const int col0 = nt * BN + cp * 64;
                     if (col0 >= p.Npad) continue;
+                    const bool full = col0 + 64 <= p.N;     // warp-uniform: no per-element key masking needed
                     if (p.pass == 1) {
+                        if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (col0 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v0[j]));
-                            if (col0 + 32 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v1[j]));
+                            for (int j = 0; j < 32; ++j)
+                                run_max = fmaxf(run_max, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (col0 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v0[j]));
+                                if (col0 + 32 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v1[j]));
+                            }
                         }
                     } else {
                         uint8_t* buf = bufs + buf_sel * kEpiBuf;
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
                         __half2 h[32];
+                        if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const float a0 = (col0 + j < p.N)
-                                                 ? exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale : 0.f;
-                            const float a1 = (col0 + j + 1 < p.N)
-                                                 ? exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
-                            const float b0 = (col0 + 32 + j < p.N)
-                                                 ? exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale : 0.f;
-                            const float b1 = (col0 + 32 + j + 1 < p.N)
-                                                 ? exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
-                            h[j >> 1] = __floats2half2_rn(a0, a1);
-                            h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
-                        }
+                            for (int j = 0; j < 32; j += 2) {
+                                const float a0 = exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale;
+                                const float a1 = exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale;
+                                const float b0 = exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale;
+                                const float b1 = exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale;
+                                h[j >> 1] = __floats2half2_rn(a0, a1);
+                                h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                run_sum += (a0 + a1) + (b0 + b1);
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 f = __half22float2(h[j]);
-                            run_sum += f.x + f.y;
+                            for (int j = 0; j < 32; j += 2) {
+                                const float a0 = (col0 + j < p.N)
+                                    ? exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                                const float a1 = (col0 + j + 1 < p.N)
+                                    ? exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                                const float b0 = (col0 + 32 + j < p.N)
+                                    ? exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                                const float b1 = (col0 + 32 + j + 1 < p.N)
+                                    ? exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                                h[j >> 1] = __floats2half2_rn(a0, a1);
+                                h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                run_sum += (a0 + a1) + (b0 + b1);
+                            }
                         }
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row
@@ -228,7 +248,8 @@ __global__ void __launch_bounds__(192, 1) gma_stats_kernel(const __grid_constant
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_3d(&args.tm_e, buf, col0, mt * BM + quad * 32, pb);
+                            // E is tile-major: [P][m-tile][64-key block][128 rows][64 keys], 16 KB per tile
+                            tma_store_3d(&args.tm_e, buf, 0, (mt * kbk + (col0 >> 6)) * BM + quad * 32, pb);
                             tma_store_commit();
                         }
                         buf_sel ^= 1;
@@ -333,9 +354,9 @@ __global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __
                 const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
                 mbar_wait(&emptyb[stage], phase ^ 1);
                 mbar_expect_tx(&fullb[stage], kTileBytes);
-                if (is_e)
-                    tma_load_3d_hint(&args.tm_e, &fullb[stage], base + stage * kTileBytes, kb * BK, mt * BM, pb,
-                                     kEvictFirst);
+                if (is_e)   // tile-major E: one contiguous 16 KB block per (m-tile, key-block)
+                    tma_load_3d_hint(&args.tm_e, &fullb[stage], base + stage * kTileBytes, 0,
+                                     static_cast<int>((static_cast<long long>(mt) * KB + kb) * BM), pb, kEvictFirst);
                 else
                     tma_load_3d_hint(&args.tm_v, &fullb[stage], base + stage * kTileBytes, kb * BK, 0, pb,
                                      kEvictLast);
@@ -486,7 +507,7 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const int grid = static_cast<int>(std::min<long long>(units, num_sms));
     prof_before(SF_KERNEL_GMA_STATS, s);
-    gma_stats_kernel<<<grid, 192, st::kSmemBytes, s>>>(args);
+    gma_stats_kernel<<<grid, st::kThreads, st::kSmemBytes, s>>>(args);
     prof_after(SF_KERNEL_GMA_STATS, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

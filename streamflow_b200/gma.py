@@ -25,7 +25,8 @@ from .corr import _aligned_workspace, _stream_ptr
 
 
 class AttentionHandle:
-    """What ``Attention.forward`` returns: E [P, N, Npad] fp16, rowsum [P, N] fp32 and the workspace."""
+    """What ``Attention.forward`` returns: E (tile-major fp16 softmax numerators, see include/streamcorr.h),
+    rowsum [P, N] fp32 and the workspace."""
 
     def __init__(self, E, rowsum, ws_buf, ws_ptr, ws_bytes, shape):
         self.E, self.rowsum = E, rowsum
@@ -39,7 +40,18 @@ class AttentionHandle:
 
     def dense(self):
         """Reference-shaped softmax matrix [P, 1, N, N] fp32 (test helper; O(N^2) memory)."""
-        return (self.E[:, :, : self.N].float() / self.rowsum[:, :, None])[:, None]
+        P, N = self.P, self.N
+        mt, npad = (N + 127) // 128, self.E.numel() // (P * ((N + 127) // 128) * 128)
+        e = self.E.view(P, mt, npad // 64, 128, 64).permute(0, 1, 3, 2, 4).reshape(P, mt * 128, npad)
+        return (e[:, :N, :N].float() / self.rowsum[:, :, None])[:, None]
+
+    def row_sums_of_e(self):
+        """sum_j E[p, i, j] in fp32 (test helper: must equal rowsum)."""
+        P, N = self.P, self.N
+        mt = (N + 127) // 128
+        npad = self.E.numel() // (P * mt * 128)
+        e = self.E.view(P, mt, npad // 64, 128, 64).float().sum(-1).sum(2)       # [P, mt, 128]
+        return e.reshape(P, mt * 128)[:, :N]
 
 
 def _check_cfg(dim, heads, dim_head):
@@ -78,7 +90,7 @@ class Attention(nn.Module):
             wq = wq.float().contiguous()
         with torch.cuda.device(dev):
             npad = L.sf_gma_npad(N)
-            E = torch.empty((P, N, npad), dtype=torch.float16, device=dev)
+            E = torch.empty((L.sf_gma_e_elems(P, N),), dtype=torch.float16, device=dev)
             rowsum = torch.empty((P, N), dtype=torch.float32, device=dev)
             ws_bytes = L.sf_gma_workspace_bytes(P, C, N, self.dim_head)
             ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)

