@@ -8,10 +8,7 @@
 //
 //   gma_stats_kernel      S = Q K^T tiles (128 x 256, K = d or 3d for hi/lo-split operands) in TMEM;
 //                         pass 1 reduces the row max, pass 2 writes E with TMA stores and the row sums.
-//   gma_aggregate_kernel  stream-K partition of all (map, query-tile, key-block) work over the SMs so every SM
-//                         streams the same number of bytes; partial 128 x 128 tiles are reduced with vector
-//                         red.global.add into an fp32 buffer.
-//   gma_finalize_kernel   out = fmap + acc * (gamma / rowsum) on the channel-major accumulator, and re-zeroes acc.
+//   gma_aggregate_kernel  (gma_aggregate_sm100.cu) the per-iteration streaming GEMM with the fused epilogue.
 #include <cuda_bf16.h>
 
 #include "sf_internal.h"
@@ -274,220 +271,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     }
 }
 
-// =====================================================================================================
-// aggregate: acc[p, n, c] += sum_j E[p, n, j] * V[p, c, j]     (stream-K)
-// =====================================================================================================
-namespace ag {
-constexpr int BM = 128, BN = 128, BK = 64;
-// E (the HBM stream) and V (L2 resident) ride separate mbarrier rings: HBM latency x 44 GB/s/SM needs ~90 KB
-// in flight per SM, so the E ring is deep and the V ring shallow.
-constexpr int kEStages = 9, kVStages = 4;
-constexpr int kTileBytes = BM * BK * 2;                  // 16 KB (E tile and V tile have the same size)
-constexpr int kSmemBytes = (kEStages + kVStages) * kTileBytes + 1024 + 512;
-constexpr int kTmemCols = 256;
-constexpr int kThreads = 224;                            // warps: 0 E-producer, 1 MMA, 2 V-producer, 3-6 epilogue
-}  // namespace ag
-
-struct GmaAggArgs {
-    CUtensorMap tm_e, tm_v;
-    GmaAggParams p;
-};
-
-__global__ void __launch_bounds__(ag::kThreads, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
-    using namespace ag;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* e_base = smem;
-    uint8_t* v_base = smem + kEStages * kTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (kEStages + kVStages) * kTileBytes);
-    uint64_t* e_full = bars;
-    uint64_t* e_empty = e_full + kEStages;
-    uint64_t* v_full = e_empty + kEStages;
-    uint64_t* v_empty = v_full + kVStages;
-    uint64_t* tfull = v_empty + kVStages;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-    const GmaAggParams& p = args.p;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long KB = p.k_blocks;
-    const long long work = static_cast<long long>(p.P) * p.m_tiles * KB;
-    const long long w_begin = work * blockIdx.x / gridDim.x;
-    const long long w_end = work * (blockIdx.x + 1) / gridDim.x;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&args.tm_e);
-        tma_prefetch_desc(&args.tm_v);
-        for (int i = 0; i < kEStages; ++i) {
-            mbar_init(&e_full[i], 1);
-            mbar_init(&e_empty[i], 1);
-        }
-        for (int i = 0; i < kVStages; ++i) {
-            mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0 || warp == 2) {
-        if (lane == 0) {
-            const bool is_e = (warp == 0);
-            const int nst = is_e ? kEStages : kVStages;
-            uint64_t* fullb = is_e ? e_full : v_full;
-            uint64_t* emptyb = is_e ? e_empty : v_empty;
-            uint8_t* base = is_e ? e_base : v_base;
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long pos = w_begin; pos < w_end; ++pos) {
-                const long long tile = pos / KB;
-                const int kb = static_cast<int>(pos - tile * KB);
-                const int pb = static_cast<int>(tile / p.m_tiles);
-                const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
-                mbar_wait(&emptyb[stage], phase ^ 1);
-                mbar_expect_tx(&fullb[stage], kTileBytes);
-                if (is_e)   // tile-major E: one contiguous 16 KB block per (m-tile, key-block)
-                    tma_load_3d_hint(&args.tm_e, &fullb[stage], base + stage * kTileBytes, 0,
-                                     static_cast<int>((static_cast<long long>(mt) * KB + kb) * BM), pb, kEvictFirst);
-                else
-                    tma_load_3d_hint(&args.tm_v, &fullb[stage], base + stage * kTileBytes, kb * BK, 0, pb,
-                                     kEvictLast);
-                if (++stage == nst) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
-            int es = 0, vs = 0, local = 0;
-            uint32_t ephase = 0, vphase = 0;
-            long long pos = w_begin;
-            while (pos < w_end) {
-                const long long tile = pos / KB;
-                const long long seg_end = min(w_end, (tile + 1) * KB);
-                const int acc = local & 1;
-                mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                bool first = true;
-                for (; pos < seg_end; ++pos) {
-                    mbar_wait(&v_full[vs], vphase);
-                    mbar_wait(&e_full[es], ephase);
-                    tc_fence_after();
-                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(e_base + es * kTileBytes));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(v_base + vs * kTileBytes));
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
-                    first = false;
-                    umma_commit(&e_empty[es]);
-                    umma_commit(&v_empty[vs]);
-                    if (++es == kEStages) {
-                        es = 0;
-                        ephase ^= 1;
-                    }
-                    if (++vs == kVStages) {
-                        vs = 0;
-                        vphase ^= 1;
-                    }
-                }
-                umma_commit(&tfull[acc]);
-                ++local;
-            }
-        }
-    } else {
-        const int quad = warp & 3;
-        int local = 0;
-        long long pos = w_begin;
-        while (pos < w_end) {
-            const long long tile = pos / KB;
-            const long long seg_end = min(w_end, (tile + 1) * KB);
-            const int pb = static_cast<int>(tile / p.m_tiles);
-            const int mt = static_cast<int>(tile - static_cast<long long>(pb) * p.m_tiles);
-            const int acc = local & 1;
-            mbar_wait(&tfull[acc], (local >> 1) & 1);
-            tc_fence_after();
-            const int row = mt * BM + quad * 32 + lane;
-            // acc is channel-major [P, 128, N] (the layout of the NCHW result): for a fixed channel the 32 lanes
-            // of a warp hit 32 consecutive floats, so every warp-level red is one fully coalesced 128 B line
-            float* dst = p.acc + static_cast<long long>(pb) * BN * p.N + row;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + ch * 32, v);
-                tmem_ld_wait();
-                if (ch == BN / 32 - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
-                }
-                if (row < p.N) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(ch * 32 + j) * p.N),
-                                     "f"(__uint_as_float(v[j]))
-                                     : "memory");
-                }
-            }
-            pos = seg_end;
-            ++local;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<kTmemCols>(tmem_base);
-    }
-}
-
-// out[p, c, n] = fmap[p, c, n] + acc[p, c, n] * (gamma / rowsum[p, n]);  acc <- 0.   Pure streaming, 4 floats/thread.
-template <typename T>
-__global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
-    const long long per_map = static_cast<long long>(p.C) * p.N;
-    const long long total = static_cast<long long>(p.P) * per_map;
-    const T* fm = reinterpret_cast<const T*>(p.fmap);
-    if ((p.N & 3) == 0) {
-        const long long total4 = total >> 2;
-        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
-             i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const long long e = i << 2;
-            const long long pb = e / per_map;
-            const int n = static_cast<int>((e - pb * per_map) % p.N);
-            float4* ap = reinterpret_cast<float4*>(p.acc + e);
-            const float4 a = *ap;
-            *ap = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 rs = __ldg(reinterpret_cast<const float4*>(p.rscale + pb * p.N + n));
-            float4 o;
-            o.x = fmaf(a.x, rs.x, static_cast<float>(fm[e + 0]));
-            o.y = fmaf(a.y, rs.y, static_cast<float>(fm[e + 1]));
-            o.z = fmaf(a.z, rs.z, static_cast<float>(fm[e + 2]));
-            o.w = fmaf(a.w, rs.w, static_cast<float>(fm[e + 3]));
-            __stcs(reinterpret_cast<float4*>(p.out + e), o);
-        }
-    } else {
-        for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < total;
-             e += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const long long pb = e / per_map;
-            const int n = static_cast<int>((e - pb * per_map) % p.N);
-            const float a = p.acc[e];
-            p.acc[e] = 0.f;
-            p.out[e] = fmaf(a, __ldg(p.rscale + pb * p.N + n), static_cast<float>(fm[e]));
-        }
-    }
-}
-
 __global__ void fill_u32_kernel(unsigned* p, unsigned v, long long n) {
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -509,38 +292,6 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     prof_before(SF_KERNEL_GMA_STATS, s);
     gma_stats_kernel<<<grid, st::kThreads, st::kSmemBytes, s>>>(args);
     prof_after(SF_KERNEL_GMA_STATS, s);
-    SF_CUDA_CHECK(cudaGetLastError());
-    return SF_OK;
-}
-
-int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
-                         cudaStream_t s) {
-    GmaAggArgs args;
-    args.tm_e = tm_e;
-    args.tm_v = tm_v;
-    args.p = p;
-    SF_CUDA_CHECK(
-        cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ag::kSmemBytes));
-    const long long work = static_cast<long long>(p.P) * p.m_tiles * p.k_blocks;
-    const int grid = static_cast<int>(std::min<long long>(work, num_sms));
-    prof_before(SF_KERNEL_GMA_AGGREGATE, s);
-    gma_aggregate_kernel<<<grid, ag::kThreads, ag::kSmemBytes, s>>>(args);
-    prof_after(SF_KERNEL_GMA_AGGREGATE, s);
-    SF_CUDA_CHECK(cudaGetLastError());
-    return SF_OK;
-}
-
-int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
-    const long long total = static_cast<long long>(p.P) * p.C * p.N;
-    const int grid = static_cast<int>(std::min<long long>((total / 4 + 255) / 256, 148 * 8));
-    prof_before(SF_KERNEL_GMA_FINALIZE, s);
-    switch (p.fmap_dtype) {
-        case SF_DT_F32: gma_finalize_kernel<float><<<grid, 256, 0, s>>>(p); break;
-        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, 256, 0, s>>>(p); break;
-        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
-        default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
-    }
-    prof_after(SF_KERNEL_GMA_FINALIZE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
