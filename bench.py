@@ -274,7 +274,7 @@ def run_ours(args):
                 arm()
             group([t["coords"][it, i] for i in range(PAIRS)])
             disarm()
-            if which in (_lib.KERNEL_GMA_AGGREGATE, _lib.KERNEL_GMA_PROJ):
+            if which in (_lib.KERNEL_GMA_AGGREGATE, _lib.KERNEL_GMA_PROJ, _lib.KERNEL_GMA_FINALIZE):
                 arm()
             agg(handle, t["mfs"])
             disarm()
@@ -286,8 +286,7 @@ def run_ours(args):
         hbm = peaks["hbm_gbs"]
         us, n = kernel_time(_lib.KERNEL_GMA_AGGREGATE)
         npad = L.sf_gma_npad(N)
-        # E stream + V (fp16) + the fused epilogue's fmap read and out write (fp32), per launch
-        bytes_agg = PAIRS * N * npad * 2 + PAIRS * CDIM * npad * 2 + 2 * PAIRS * CDIM * N * 4
+        bytes_agg = PAIRS * N * npad * 2 + PAIRS * CDIM * npad * 2           # E stream + V, per launch
         kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / us / 1e3, "peak": hbm, "unit": "GB/s",
                                     "frac": bytes_agg / us / 1e3 / hbm, "us_per_launch": us, "launches_timed": n,
                                     "algorithmic_bytes": bytes_agg, "traffic": None,
@@ -311,7 +310,8 @@ def run_ours(args):
 
         # the small helper kernels, for the step budget in DESIGN.md (event pair brackets the last launch of the
         # kind inside each public call)
-        for name, kind in (("gma_proj_v", _lib.KERNEL_GMA_PROJ), ("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
+        for name, kind in (("gma_proj_v", _lib.KERNEL_GMA_PROJ), ("gma_finalize", _lib.KERNEL_GMA_FINALIZE),
+                           ("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
             us, n = kernel_time(kind)
             kernels[name] = {"us_per_launch": us, "launches_timed": n}
 

@@ -115,7 +115,7 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
  * sf_gma_aggregate computes every iteration
  *     out = fmap + gamma * ((E / rowsum) . (W_v . fmap)^T).
  * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) must be the SAME buffer for the attention call
- * and all aggregate calls that use its E: it holds the split-tile counters the aggregate keeps zeroed.       */
+ * and all aggregate calls that use its E: it holds the fp32 accumulation buffer the aggregate keeps zeroed. */
 SF_API int64_t sf_gma_npad(int64_t N);
 SF_API int64_t sf_gma_e_elems(int64_t P, int64_t N);
 SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);

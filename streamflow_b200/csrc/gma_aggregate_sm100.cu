@@ -1,22 +1,22 @@
-// G3b: per-iteration GMA aggregation (core/gma.py:91-104) as ONE streaming tcgen05 GEMM with a fused epilogue:
+// G3b: per-iteration GMA aggregation (core/gma.py:91-104) as a streaming tcgen05 GEMM
 //
-//     out[p, c, n] = fmap[p, c, n] + (gamma / rowsum[p, n]) * sum_j E[p, n, j] * V[p, c, j]
+//     acc[p, c, n] += sum_j E[p, n, j] * V[p, c, j]          (gma_aggregate_kernel, this file)
+//     out[p, c, n]  = fmap[p, c, n] + acc[p, c, n] * gamma / rowsum[p, n];  acc <- 0     (gma_finalize_kernel)
 //
 // HBM-bound on the fp16 softmax numerators E (297 MB per Sintel clip and iteration).  Design points:
 //   * one CTA owns TWO 128-query tiles (M = 256) per key block, so each 16 KB V tile fetched from L2 feeds two MMAs:
 //     SM ingest is 1.5 B per E byte instead of 2 -- with M = 128 the kernel sat on the L2->SM bandwidth cap
-//     (measured: 10.4 TB/s of L2 reads for 4.9 TB/s of HBM), not on HBM;
+//     (measured: ~10.4 TB/s of L2 reads for 4.9 TB/s of HBM), not on HBM;
 //   * stream-K: the linear (map, tile-pair, key-block) space is cut into gridDim equal contiguous ranges, so every SM
 //     streams the same number of bytes (165 tiles over 148 SMs would otherwise quantise to 2 waves);
 //   * E tiles are 16 KB contiguous blocks (tile-major layout written by gma_stats_kernel) on a deep mbarrier ring
 //     (5 x 32 KB in flight per SM), V on a shallow one (3 x 16 KB);
-//   * split tiles are reduced with the stream-K "last arriver" fix-up: every contributor parks its fp32 partial
-//     (coalesced, channel-major) in a per-CTA slot, bumps the tile's counter, and the CTA that arrives last sums the
-//     slots and runs the real epilogue -- residual add, gamma / rowsum scale and the NCHW store happen in-kernel,
-//     so there is no accumulator zeroing, no atomics on the data and no separate finalize pass.
+//   * split tiles are reduced with red.global.add.f32 into a channel-major fp32 buffer: thread = query row, so for
+//     each channel the 32 lanes of a warp hit one 128 B line.  (A fused "last arriver" fix-up epilogue was tried
+//     and rejected: with in-order stream-K every CTA ends on a shared tile, so the 512 KB/tile fix-up traffic is
+//     issued by 128 threads at the very end of the kernel, latency-bound and fully exposed -- 159 us vs 62 us.)
 //
-// warps: 0 = E producer (TMA), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-6 = epilogue (one TMEM lane
-// quadrant each; thread = query row, loop over channels -> every global access is a coalesced 128 B line).
+// warps: 0 = E producer (TMA), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-6 = epilogue.
 #include <cuda_bf16.h>
 
 #include "sf_internal.h"
@@ -33,29 +33,12 @@ constexpr int kEStageBytes = 2 * kTileBytes;                     // two query ti
 constexpr int kSmemBytes = kEStages * kEStageBytes + kVStages * kTileBytes + 1024 + 512;
 constexpr int kTmemCols = 512;                                   // 2 buffers x (2 tiles x 128 columns)
 constexpr int kThreads = 224;
-constexpr int kPartialFloats = 2 * BM * BN;                      // one parked partial: [128 ch][256 rows] fp32
 
 struct GmaAggArgs {
     CUtensorMap tm_e, tm_v;
     GmaAggParams p;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-template <typename T>
-__device__ __forceinline__ float to_float(T v) {
-    return static_cast<float>(v);
-}
-template <>
-__device__ __forceinline__ float to_float<__half>(__half v) {
-    return __half2float(v);
-}
-template <>
-__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) {
-    return __bfloat162float(v);
-}
-
-template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -69,7 +52,6 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     uint64_t* tfull = v_empty + kVStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
 
     const GmaAggParams& p = args.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,111 +171,39 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         }
     } else {                                                   // ---- epilogue (warps 3-6)
         const int quad = warp & 3;
-        const int et = threadIdx.x - 96;                       // 0..127 among the epilogue threads
-        const T* fmap = reinterpret_cast<const T*>(p.fmap);
         int local = 0;
         long long pos = w_begin;
-        auto owner = [&](long long u) { return ((u + 1) * G - 1) / work; };   // CTA whose range holds unit u
         while (pos < w_end) {
             const long long pt = pos / KB;
             const long long seg_end = min(w_end, (pt + 1) * KB);
             const int pb = static_cast<int>(pt / p.pair_tiles);
             const int mp = static_cast<int>(pt - static_cast<long long>(pb) * p.pair_tiles);
-            const long long first_cta = owner(pt * KB), last_cta = owner((pt + 1) * KB - 1);
-            const int contributors = static_cast<int>(last_cta - first_cta + 1);
             const int acc = local & 1;
             mbar_wait(&tfull[acc], (local >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (2 * BN);
-            const float* chan_base_dummy = nullptr;
-            (void)chan_base_dummy;
-
-            if (contributors == 1) {
-                // whole tile pair accumulated here: epilogue straight from TMEM
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int n = (2 * mp + half) * BM + quad * 32 + lane;
-                    const bool ok = n < p.N;
-                    const float rs = ok ? __ldg(p.rscale + static_cast<long long>(pb) * p.N + n) : 0.f;
-                    const long long base = static_cast<long long>(pb) * BN * p.N + n;
+            for (int half = 0; half < 2; ++half) {
+                const int n = (2 * mp + half) * BM + quad * 32 + lane;
+                // acc is channel-major [P, 128, N] (the layout of the NCHW result): for a fixed channel the 32
+                // lanes of a warp hit 32 consecutive floats, so every warp-level red is one coalesced 128 B line
+                float* dst = p.acc + static_cast<long long>(pb) * BN * p.N + n;
 #pragma unroll 1
-                    for (int ch = 0; ch < BN / 32; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_acc + half * BN + ch * 32, v);
-                        tmem_ld_wait();
-                        if (half == 1 && ch == BN / 32 - 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);
-                        }
-                        if (ok) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const long long idx = base + static_cast<long long>(ch * 32 + j) * p.N;
-                                __stcs(p.out + idx, fmaf(__uint_as_float(v[j]), rs, to_float<T>(fmap[idx])));
-                            }
-                        }
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + half * BN + ch * 32, v);
+                    tmem_ld_wait();
+                    if (half == 1 && ch == BN / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
                     }
-                }
-            } else {
-                // park this CTA's partial: slot 0 if this is the first tile pair the CTA touches, else slot 1
-                const int which = (w_begin / KB == pt) ? 0 : 1;
-                float* mine = p.partials + (static_cast<long long>(blockIdx.x) * 2 + which) * kPartialFloats;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    float* dst = mine + half * BM + quad * 32 + lane;      // [channel][256 rows]: lanes contiguous
-#pragma unroll 1
-                    for (int ch = 0; ch < BN / 32; ++ch) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_acc + half * BN + ch * 32, v);
-                        tmem_ld_wait();
-                        if (half == 1 && ch == BN / 32 - 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);
-                        }
+                    if (n < p.N) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) __stcg(dst + (ch * 32 + j) * (2 * BM), __uint_as_float(v[j]));
-                    }
-                }
-                // publish, and find out whether every other contributor has already published
-                epi_bar_sync();
-                if (et == 0) {
-                    __threadfence();
-                    const int prev = atomicAdd(p.counters + pt, 1);
-                    const int last = (prev == contributors - 1);
-                    if (last) p.counters[pt] = 0;                         // ready for the next launch
-                    __threadfence();
-                    *s_last = last;
-                }
-                epi_bar_sync();
-                const int is_last = *s_last;
-                epi_bar_sync();                                            // s_last may be rewritten next segment
-                if (is_last) {
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        const int n = (2 * mp + half) * BM + quad * 32 + lane;
-                        if (n >= p.N) continue;
-                        const float rs = __ldg(p.rscale + static_cast<long long>(pb) * p.N + n);
-                        const long long base = static_cast<long long>(pb) * BN * p.N + n;
-                        const int roff = half * BM + quad * 32 + lane;
-#pragma unroll 1
-                        for (int c0 = 0; c0 < BN; c0 += 16) {
-                            float sum[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) sum[j] = 0.f;
-                            for (long long cta = first_cta; cta <= last_cta; ++cta) {
-                                const int wh = ((work * cta / G) / KB == pt) ? 0 : 1;
-                                const float* src = p.partials + (cta * 2 + wh) * kPartialFloats + roff;
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) sum[j] += __ldcg(src + (c0 + j) * (2 * BM));
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const long long idx = base + static_cast<long long>(c0 + j) * p.N;
-                                __stcs(p.out + idx, fmaf(sum[j], rs, to_float<T>(fmap[idx])));
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(ch * 32 + j) * p.N),
+                                         "f"(__uint_as_float(v[j]))
+                                         : "memory");
                     }
                 }
             }
@@ -310,12 +220,37 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     }
 }
 
-}  // namespace
-
-int gma_aggregate_max_ctas() { return 160; }
-long long gma_aggregate_partial_bytes() {
-    return static_cast<long long>(gma_aggregate_max_ctas()) * 2 * kPartialFloats * sizeof(float);
+// out[p, c, n] = fmap[p, c, n] + acc[p, c, n] * (gamma / rowsum[p, n]);  acc <- 0.
+// grid = (ceil(N / 1024), P * C): one float4 per thread, no index arithmetic, every load in flight at once.
+template <typename T>
+__global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
+    const int row = blockIdx.y;                          // p * C + c
+    const int pb = row / p.C;
+    const long long base = static_cast<long long>(row) * p.N;
+    const T* fm = reinterpret_cast<const T*>(p.fmap) + base;
+    float* acc = p.acc + base;
+    float* out = p.out + base;
+    const float* rs = p.rscale + static_cast<long long>(pb) * p.N;
+    const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (n >= p.N) return;
+    if ((p.N & 3) == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(acc + n);
+        const float4 r = __ldg(reinterpret_cast<const float4*>(rs + n));
+        const float f0 = static_cast<float>(fm[n]), f1 = static_cast<float>(fm[n + 1]);
+        const float f2 = static_cast<float>(fm[n + 2]), f3 = static_cast<float>(fm[n + 3]);
+        *reinterpret_cast<float4*>(acc + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __stcs(reinterpret_cast<float4*>(out + n),
+               make_float4(fmaf(a.x, r.x, f0), fmaf(a.y, r.y, f1), fmaf(a.z, r.z, f2), fmaf(a.w, r.w, f3)));
+    } else {
+        for (int e = n; e < min(n + 4, p.N); ++e) {
+            const float a = acc[e];
+            acc[e] = 0.f;
+            out[e] = fmaf(a, __ldg(rs + e), static_cast<float>(fm[e]));
+        }
+    }
 }
+
+}  // namespace
 
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
                          cudaStream_t s) {
@@ -324,21 +259,27 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
     args.tm_v = tm_v;
     args.p = p;
     const long long work = static_cast<long long>(p.P) * p.pair_tiles * p.k_blocks;
-    const int grid = static_cast<int>(std::min<long long>(work, std::min(num_sms, gma_aggregate_max_ctas())));
-    auto launch = [&](auto kernel) -> int {
-        SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        prof_before(SF_KERNEL_GMA_AGGREGATE, s);
-        kernel<<<grid, kThreads, kSmemBytes, s>>>(args);
-        prof_after(SF_KERNEL_GMA_AGGREGATE, s);
-        SF_CUDA_CHECK(cudaGetLastError());
-        return SF_OK;
-    };
+    const int grid = static_cast<int>(std::min<long long>(work, num_sms));
+    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    prof_before(SF_KERNEL_GMA_AGGREGATE, s);
+    gma_aggregate_kernel<<<grid, kThreads, kSmemBytes, s>>>(args);
+    prof_after(SF_KERNEL_GMA_AGGREGATE, s);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
+    dim3 grid((p.N + 1023) / 1024, p.P * p.C);
+    prof_before(SF_KERNEL_GMA_FINALIZE, s);
     switch (p.fmap_dtype) {
-        case SF_DT_F32: return launch(gma_aggregate_kernel<float>);
-        case SF_DT_F16: return launch(gma_aggregate_kernel<__half>);
-        case SF_DT_BF16: return launch(gma_aggregate_kernel<__nv_bfloat16>);
-        default: set_error("gma_aggregate: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
+        case SF_DT_F32: gma_finalize_kernel<float><<<grid, 256, 0, s>>>(p); break;
+        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, 256, 0, s>>>(p); break;
+        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+        default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
     }
+    prof_after(SF_KERNEL_GMA_FINALIZE, s);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
 }
 
 }  // namespace sf

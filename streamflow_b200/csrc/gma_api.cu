@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, v_off, partials_off, counters_off, rscale_off, total;
+    int64_t q_off, k_off, rowmax_off, v_off, acc_off, rscale_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -19,8 +19,7 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.k_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
     ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
-    ws.partials_off = off; off += align_up(gma_aggregate_partial_bytes(), 1024);
-    ws.counters_off = off; off += align_up(P * (((N + 127) / 128 + 1) / 2) * 4, 1024);
+    ws.acc_off = off;     off += align_up(P * N * d * 4, 1024);
     ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
     ws.total = off;
     return ws;
@@ -84,7 +83,7 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
 
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
     SF_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, P * N * 4, s));
-    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.counters_off, 0, P * (((N + 127) / 128 + 1) / 2) * 4, s));
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.acc_off, 0, P * N * d * 4, s));
 
     CUtensorMap tm_q, tm_k, tm_e;
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
@@ -151,12 +150,12 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     ap.m_tiles = (int)((N + 127) / 128);
     ap.pair_tiles = (ap.m_tiles + 1) / 2;
     ap.k_blocks = (int)(Npad / 64);
-    ap.partials = reinterpret_cast<float*>(wsb + ws.partials_off);
-    ap.counters = reinterpret_cast<int*>(wsb + ws.counters_off);
+    ap.acc = reinterpret_cast<float*>(wsb + ws.acc_off);
     ap.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
     ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
     ap.out = out;
-    return launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s);
+    if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
+    return launch_gma_finalize(ap, s);
 }
 
 }  // extern "C"

@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                                 const float b1 = exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale;
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
-                                run_sum += (a0 + a1) + (b0 + b1);
                             }
                         } else {
 #pragma unroll
@@ -230,8 +229,13 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                                     ? exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
-                                run_sum += (a0 + a1) + (b0 + b1);
                             }
+                        }
+                        // row sum of the ROUNDED numerators (fp32 adds): sum_j E / rowsum == 1 for what is stored
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 f = __half22float2(h[j]);
+                            run_sum += f.x + f.y;
                         }
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row

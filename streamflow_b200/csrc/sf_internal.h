@@ -150,17 +150,15 @@ struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
     int m_tiles, pair_tiles;    // ceil(N/128), ceil(m_tiles/2): one CTA work item covers two query tiles
     int k_blocks;               // Npad / 64
-    float* partials;            // [max_ctas][2][128 ch][256 rows] fp32 parking slots for split tile pairs
-    int* counters;              // [P * pair_tiles], zero between launches
+    float* acc;                 // [P, 128, N] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
     const float* rscale;        // [P, N] gamma / rowsum (written by the v projection)
     const void* fmap;           // [P, C, N]
     int fmap_dtype;
     float* out;                 // [P, C, N]
 };
-int gma_aggregate_max_ctas();
-long long gma_aggregate_partial_bytes();
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
                          cudaStream_t s);
+int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s);
 int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
 
 }  // namespace sf
