@@ -1,0 +1,83 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/streamcorr.h
+declares, answers its pure-host queries, and refuses to compute without an sm_100 device (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from streamflow_b200.build import build_library
+    build_library()
+    import streamflow_b200
+    return streamflow_b200.lib()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "streamcorr.h")).read()
+    return sorted(set(re.findall(r"SF_API\s+[\w\s\*]+?\b(sf_\w+)\s*\(", text)))
+
+
+def test_exports_every_header_symbol(L):
+    from streamflow_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 14
+    for name in syms:
+        assert hasattr(L, name), f"libstreamcorr.so does not export {name}"
+    assert sorted(_lib.EXPORTS) == syms, "streamflow_b200/_lib.py EXPORTS out of sync with the header"
+
+
+def test_version_and_level_geometry(L):
+    from streamflow_b200 import _lib
+    assert L.sf_version() == 100
+    # Sintel 55x128 and BASELINE configs[0] 46x62 (floor-mode pooling, pitch rounded up to 4 floats)
+    assert [_lib.level_dims(55, 128, l) for l in range(4)] == [(55, 128, 128), (27, 64, 64), (13, 32, 32), (6, 16, 16)]
+    assert [_lib.level_dims(46, 62, l) for l in range(4)] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
+    assert L.sf_gma_npad(7040) == 7040 and L.sf_gma_npad(2852) == 2880
+    assert L.sf_gma_e_elems(3, 7040) == 3 * 7040 * 7040
+    assert L.sf_gma_e_elems(1, 2852) == 2944 * 2880
+
+
+def test_workspace_queries(L):
+    from streamflow_b200 import _lib
+    n = 55 * 128
+    w16 = L.sf_corr_workspace_bytes(1, 256, 55, 128, _lib.PREC_F16)
+    w32 = L.sf_corr_workspace_bytes(1, 256, 55, 128, _lib.PREC_F16X2)
+    assert w16 >= 2 * (n + 9280) * 256 and w32 >= 3 * (w16 - 4096) - 8192
+    assert L.sf_corr_workspace_bytes(1, 256, 55, 128, _lib.PREC_FP32_SIMT) >= 2 * 4 * 256 * n
+    assert L.sf_corr_workspace_bytes(0, 256, 55, 128, 0) == 0
+    assert L.sf_gma_workspace_bytes(3, 128, n, 128) > 3 * n * 128 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_device_means_loud_failure(L):
+    from streamflow_b200 import Aggregate, Attention, CorrBlock, StreamCorrError
+    assert L.sf_device_ok() != 0
+    assert b"no CPU fallback" in L.sf_last_error() or b"no fallback" in L.sf_last_error()
+    x = torch.zeros(1, 8, 16, 16)
+    with pytest.raises(StreamCorrError):
+        CorrBlock(x, x)
+
+    class A:
+        pass
+    with pytest.raises(StreamCorrError):
+        Attention(args=A(), dim=128, heads=1, dim_head=128)(torch.zeros(1, 128, 8, 8))
+    with pytest.raises(StreamCorrError):
+        Aggregate(args=A(), dim=128, heads=1, dim_head=128)(None, torch.zeros(1, 128, 8, 8))
+    # the raw entry points also fail (return code, not a crash)
+    import ctypes
+    lv = (ctypes.c_void_p * 4)(1024, 1024, 1024, 1024)
+    assert L.sf_corr_lookup(lv, 1024, 1024, 1, 16, 16, 4, 4, None) != 0
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under streamflow_b200/ may import it."""
+    pkg = os.path.join(ROOT, "streamflow_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, f"{fn} references the oracle"
