@@ -60,10 +60,15 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
     float m = 0.f;
     for (int b = 0; b < B; ++b) {
         const float4* v = reinterpret_cast<const float4*>(f + b * sb);
-        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-             i += static_cast<long long>(gridDim.x) * blockDim.x) {
-            const float4 q = __ldg(v + i);
-            m = fmaxf(fmaxf(m, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += 4 * stride) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)     // four independent 16-byte loads in flight per thread
+                q[u] = (i + u * stride < n4) ? __ldg(v + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                m = fmaxf(fmaxf(m, fmaxf(fabsf(q[u].x), fabsf(q[u].y))), fmaxf(fabsf(q[u].z), fabsf(q[u].w)));
         }
     }
 #pragma unroll
@@ -71,52 +76,13 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
 }
 
-__device__ __forceinline__ float src_at(const PackSeg& s, long long boff, int k, int y, int x) {
-    return __ldg(s.src + boff + k * s.sk + y * s.sy + x * s.sx);
-}
-
-// 2x2 average pooling applied `level` times (floor mode): same nesting as the reference's repeated avg_pool2d.
-__device__ float pooled_at(const PackSeg& s, long long boff, int k, int v, int u) {
-    if (s.level == 0) return src_at(s, boff, k, v, u);
-    if (s.level == 1) {
-        const int y = 2 * v, x = 2 * u;
-        return 0.25f * ((src_at(s, boff, k, y, x) + src_at(s, boff, k, y, x + 1)) +
-                        (src_at(s, boff, k, y + 1, x) + src_at(s, boff, k, y + 1, x + 1)));
-    }
-    const int half = 1 << (s.level - 1);     // side of the level-(l-1) block in source pixels
-    float quad[4];
-#pragma unroll
-    for (int qy = 0; qy < 2; ++qy)
-#pragma unroll
-        for (int qx = 0; qx < 2; ++qx) {
-            // value of the level-(l-1) cell (2v+qy, 2u+qx)
-            const int y0 = (2 * v + qy) * half, x0 = (2 * u + qx) * half;
-            float acc;
-            if (s.level == 2) {
-                acc = 0.25f * ((src_at(s, boff, k, y0, x0) + src_at(s, boff, k, y0, x0 + 1)) +
-                               (src_at(s, boff, k, y0 + 1, x0) + src_at(s, boff, k, y0 + 1, x0 + 1)));
-            } else {   // level 3: cell is a 4x4 source block = 2x2 of 2x2 averages
-                float sub[4];
-#pragma unroll
-                for (int sy = 0; sy < 2; ++sy)
-#pragma unroll
-                    for (int sx = 0; sx < 2; ++sx) {
-                        const int yy = y0 + 2 * sy, xx = x0 + 2 * sx;
-                        sub[sy * 2 + sx] =
-                            0.25f * ((src_at(s, boff, k, yy, xx) + src_at(s, boff, k, yy, xx + 1)) +
-                                     (src_at(s, boff, k, yy + 1, xx) + src_at(s, boff, k, yy + 1, xx + 1)));
-                    }
-                acc = 0.25f * ((sub[0] + sub[1]) + (sub[2] + sub[3]));
-            }
-            quad[qy * 2 + qx] = acc;
-        }
-    return 0.25f * ((quad[0] + quad[1]) + (quad[2] + quad[3]));
-}
-
 // CTA = 32 rows x 64 channels of one segment / batch element.  blockDim = (32, 8).
+// Index arithmetic is done once per row (pixel offset) in shared memory; the per-element work is one add, the
+// loads of the 2^l x 2^l pooling block and one multiply (the first version spent ~110 instructions per element
+// on 64-bit stride arithmetic and was issue-bound at 37 us).
 __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ PackParams p) {
     __shared__ float tile[64][33];
-    __shared__ int s_v[32], s_u[32];
+    __shared__ long long s_pix[32];     // element offset of the top-left source pixel of the row's pooling block
     __shared__ float s_scale;
 
     int si = 0;
@@ -127,18 +93,20 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     const int row0 = (static_cast<int>(blockIdx.x) - s.tile0) * 32;
     const int k0 = blockIdx.y * 64;
     const int b = blockIdx.z;
-    const long long boff = b * s.sb;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const bool kfast = (s.sk == 1);
-    if (ty == 0) {      // one division per row and ONE read of the scale word per CTA (no same-address hot spot)
+    const int level = s.level;
+    if (ty == 0) {
         const int m = row0 + tx;
-        const int v = m / s.pitch;
-        s_v[tx] = v;
-        s_u[tx] = m - v * s.pitch;
+        const int v = m / s.pitch, u = m - v * s.pitch;
+        const bool ok = (m < s.rows) && (u < s.wl);
+        s_pix[tx] = ok ? (static_cast<long long>(v << level) * s.sy + static_cast<long long>(u << level) * s.sx) : -1;
         if (tx == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[s.amax_slot])));
     }
     __syncthreads();
-    const float scale = s_scale;
+    const float* src = s.src + b * s.sb;
+    const int side = 1 << level;
+    const float scale = s_scale / static_cast<float>(side * side);
 
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -150,11 +118,19 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
             rr = tx;
             kk = ty + 8 * it;
         }
-        const int m = row0 + rr;
+        const long long pix = s_pix[rr];
         float val = 0.f;
-        if (m < s.rows && k0 + kk < p.D) {
-            const int v = s_v[rr], u = s_u[rr];
-            if (u < s.wl) val = pooled_at(s, boff, k0 + kk, v, u) * scale;
+        if (pix >= 0 && k0 + kk < p.D) {
+            const float* q = src + pix + static_cast<long long>(k0 + kk) * s.sk;
+            if (level == 0) {
+                val = __ldg(q);
+            } else {
+                // mean over the 2^l x 2^l block == l nested 2x2 average pools (floor mode); exact up to fp32
+                // summation order, far below the fp16 operand rounding that follows
+                for (int dy = 0; dy < side; ++dy)
+                    for (int dx = 0; dx < side; ++dx) val += __ldg(q + dy * s.sy + dx * s.sx);
+            }
+            val *= scale;
         }
         tile[kk][rr] = val;
     }
