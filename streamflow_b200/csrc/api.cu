@@ -241,30 +241,19 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     if (int rc = launch_absmax2(fmap1, fmap2, B, D, h, w, f1_strides, f2_strides, amax, s)) return rc;
 
     PackParams pp{};
-    pp.nseg = 1 + SF_NUM_LEVELS;
-    pp.D = static_cast<int>(D);
+    pp.src[0] = fmap1; pp.src[1] = fmap2;
+    pp.sb[0] = f1_strides[0]; pp.sk[0] = f1_strides[1]; pp.sy[0] = f1_strides[2]; pp.sx[0] = f1_strides[3];
+    pp.sb[1] = f2_strides[0]; pp.sk[1] = f2_strides[1]; pp.sy[1] = f2_strides[2]; pp.sx[1] = f2_strides[3];
+    pp.dst_a = reinterpret_cast<__half*>(wsb + ws.a_off);
+    pp.h = (int)h; pp.w = (int)w; pp.D = (int)D;
     pp.split = (precision == SF_PREC_F16X2);
-    pp.amax_bits = amax;
-    int tile = 0;
-    {
-        PackSeg& a = pp.seg[0];
-        a.src = fmap1;
-        a.sb = f1_strides[0]; a.sk = f1_strides[1]; a.sy = f1_strides[2]; a.sx = f1_strides[3];
-        a.dst = reinterpret_cast<__half*>(wsb + ws.a_off);
-        a.hl = (int)h; a.wl = (int)w; a.pitch = (int)w; a.level = 0;
-        a.rows = (int)N; a.tile0 = tile; a.amax_slot = 0; a.is_b = 0;
-        tile += (a.rows + 31) / 32;
-    }
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
-        PackSeg& b = pp.seg[1 + l];
-        b.src = fmap2;
-        b.sb = f2_strides[0]; b.sk = f2_strides[1]; b.sy = f2_strides[2]; b.sx = f2_strides[3];
-        b.dst = reinterpret_cast<__half*>(wsb + ws.b_off[l]);
-        b.hl = g.h[l]; b.wl = g.w[l]; b.pitch = g.pitch[l]; b.level = l;
-        b.rows = (int)g.img[l]; b.tile0 = tile; b.amax_slot = 1; b.is_b = 1;
-        tile += (b.rows + 31) / 32;
+        pp.dst_b[l] = reinterpret_cast<__half*>(wsb + ws.b_off[l]);
+        pp.hl[l] = g.h[l]; pp.wl[l] = g.w[l]; pp.pitch[l] = g.pitch[l]; pp.rows[l] = (int)g.img[l];
     }
-    if (int rc = launch_corr_pack(pp, tile, B, s)) return rc;
+    pp.bx = (int)((w + 7) / 8); pp.by = (int)((h + 7) / 8);
+    pp.amax_bits = amax;
+    if (int rc = launch_corr_pack(pp, B, s)) return rc;
 
     CorrGemmParams gp{};
     gp.B = (int)B; gp.N = (int)N; gp.Kp = ws.Kp;

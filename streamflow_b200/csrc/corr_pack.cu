@@ -76,84 +76,118 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
 }
 
-// CTA = 32 rows x 64 channels of one segment / batch element.  blockDim = (32, 8).
-// Index arithmetic is done once per row (pixel offset) in shared memory; the per-element work is one add, the
-// loads of the 2^l x 2^l pooling block and one multiply (the first version spent ~110 instructions per element
-// on 64-bit stride arithmetic and was issue-bound at 37 us).
+// CTA = one 8x8 source-pixel block x 64 channels of fmap1 (operand A) or fmap2 (operands B_0..B_3).
+// Every source value is loaded ONCE; the three pooled levels are built hierarchically in shared memory with
+// the reference's own nesting (avg_pool2d applied l times, floor mode), so a block yields 64 / 16 / 4 / 1 operand
+// rows of levels 0 / 1 / 2 / 3.  (The first version gathered 4^l source pixels per pooled element: the level-3
+// rows lived in 12 CTAs with 512 serial loads per thread and set the kernel time at 37-46 us.)
 __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ PackParams p) {
-    __shared__ float tile[64][33];
-    __shared__ long long s_pix[32];     // element offset of the top-left source pixel of the row's pooling block
+    __shared__ float t0[64][65];
+    __shared__ float t1[16][65];
+    __shared__ float t2[4][65];
+    __shared__ float t3[1][65];
     __shared__ float s_scale;
 
-    int si = 0;
-#pragma unroll
-    for (int i = 1; i < 1 + SF_NUM_LEVELS; ++i)
-        if (i < p.nseg && static_cast<int>(blockIdx.x) >= p.seg[i].tile0) si = i;
-    const PackSeg& s = p.seg[si];
-    const int row0 = (static_cast<int>(blockIdx.x) - s.tile0) * 32;
-    const int k0 = blockIdx.y * 64;
-    const int b = blockIdx.z;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const bool kfast = (s.sk == 1);
-    const int level = s.level;
-    if (ty == 0) {
-        const int m = row0 + tx;
-        const int v = m / s.pitch, u = m - v * s.pitch;
-        const bool ok = (m < s.rows) && (u < s.wl);
-        s_pix[tx] = ok ? (static_cast<long long>(v << level) * s.sy + static_cast<long long>(u << level) * s.sx) : -1;
-        if (tx == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[s.amax_slot])));
-    }
+    const int tid = threadIdx.x;
+    const int which = blockIdx.z & 1;              // 0: A from fmap1, 1: B levels from fmap2
+    const int b = blockIdx.z >> 1;
+    const int byi = blockIdx.x / p.bx, bxi = blockIdx.x - byi * p.bx;
+    const int y0 = byi * 8, x0 = bxi * 8, k0 = blockIdx.y * 64;
+    const long long sk = p.sk[which], sy = p.sy[which], sx = p.sx[which];
+    const float* src = p.src[which] + b * p.sb[which];
+    if (tid == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[which])));
     __syncthreads();
-    const float* src = s.src + b * s.sb;
-    const int side = 1 << level;
-    const float scale = s_scale / static_cast<float>(side * side);
+    const float scale = s_scale;
 
+    const bool vec = (sk == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((p.sb[which] & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.src[which]) & 15) == 0) && (k0 + 64 <= p.D);
+    if (vec) {
+        float4 q[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        int kk, rr;
-        if (kfast) {
-            kk = tx + 32 * (it & 1);
-            rr = ty + 8 * (it >> 1);
-        } else {
-            rr = tx;
-            kk = ty + 8 * it;
+        for (int it = 0; it < 4; ++it) {           // 16 threads x float4 = the 64 channels of one pixel (256 B)
+            const int px = (tid >> 4) + 16 * it;
+            const int y = y0 + (px >> 3), x = x0 + (px & 7);
+            q[it] = (y < p.h && x < p.w) ? __ldg(reinterpret_cast<const float4*>(src + y * sy + x * sx + k0) + (tid & 15))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const long long pix = s_pix[rr];
-        float val = 0.f;
-        if (pix >= 0 && k0 + kk < p.D) {
-            const float* q = src + pix + static_cast<long long>(k0 + kk) * s.sk;
-            if (level == 0) {
-                val = __ldg(q);
-            } else {
-                // mean over the 2^l x 2^l block == l nested 2x2 average pools (floor mode); exact up to fp32
-                // summation order, far below the fp16 operand rounding that follows
-                for (int dy = 0; dy < side; ++dy)
-                    for (int dx = 0; dx < side; ++dx) val += __ldg(q + dy * s.sy + dx * s.sx);
-            }
-            val *= scale;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int px = (tid >> 4) + 16 * it, c = 4 * (tid & 15);
+            t0[px][c + 0] = q[it].x * scale;
+            t0[px][c + 1] = q[it].y * scale;
+            t0[px][c + 2] = q[it].z * scale;
+            t0[px][c + 3] = q[it].w * scale;
         }
-        tile[kk][rr] = val;
+    } else {
+        const bool xfast = (sx == 1);
+#pragma unroll 4
+        for (int i = tid; i < 64 * 64; i += 256) {
+            const int px = xfast ? (i & 63) : (i >> 6);
+            const int kk = xfast ? (i >> 6) : (i & 63);
+            const int y = y0 + (px >> 3), x = x0 + (px & 7);
+            float v = 0.f;
+            if (y < p.h && x < p.w && k0 + kk < p.D) v = __ldg(src + y * sy + x * sx + (k0 + kk) * sk) * scale;
+            t0[px][kk] = v;
+        }
     }
     __syncthreads();
+
+    if (which == 1) {   // pooled levels, nested exactly like the reference: level l+1 = avg_pool2d(level l, 2, 2)
+        for (int i = tid; i < 16 * 64; i += 256) {
+            const int c = i >> 6, kk = i & 63, cy = c >> 2, cx = c & 3;
+            const int o = (2 * cy) * 8 + 2 * cx;
+            t1[c][kk] = (((t0[o][kk] + t0[o + 1][kk]) + t0[o + 8][kk]) + t0[o + 9][kk]) * 0.25f;
+        }
+        __syncthreads();
+        {
+            const int c = tid >> 6, kk = tid & 63, cy = c >> 1, cx = c & 1;
+            const int o = (2 * cy) * 4 + 2 * cx;
+            t2[c][kk] = (((t1[o][kk] + t1[o + 1][kk]) + t1[o + 4][kk]) + t1[o + 5][kk]) * 0.25f;
+        }
+        __syncthreads();
+        if (tid < 64) t3[0][tid] = (((t2[0][tid] + t2[1][tid]) + t2[2][tid]) + t2[3][tid]) * 0.25f;
+        __syncthreads();
+    }
 
     const int Kp = p.split ? 3 * p.D : p.D;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int rr = ty + 8 * it;
-        const int m = row0 + rr;
-        const int kk = 2 * tx;
-        if (m >= s.rows || k0 + kk >= p.D) continue;
-        const float v0 = tile[kk][rr], v1 = tile[kk + 1][rr];
-        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-        __half* drow = s.dst + (static_cast<long long>(b) * s.rows + m) * Kp + k0 + kk;
-        *reinterpret_cast<__half2*>(drow) = __halves2half2(h0, h1);
-        if (p.split) {
-            const float l0 = (v0 - __half2float(h0)) * 2048.f, l1 = (v1 - __half2float(h1)) * 2048.f;
-            const __half2 lo = __halves2half2(__float2half_rn(l0), __float2half_rn(l1));
-            const __half2 hs = __halves2half2(__float2half_rn(__half2float(h0) * (1.f / 2048.f)),
-                                              __float2half_rn(__half2float(h1) * (1.f / 2048.f)));
-            *reinterpret_cast<__half2*>(drow + p.D) = s.is_b ? lo : hs;
-            *reinterpret_cast<__half2*>(drow + 2 * p.D) = s.is_b ? hs : lo;
+    const int nlev = which ? SF_NUM_LEVELS : 1;
+    for (int l = 0; l < nlev; ++l) {
+        const int side = 8 >> l;                                   // cells per block edge at this level
+        const int hl = which ? p.hl[l] : p.h, wl = which ? p.wl[l] : p.w;
+        const int pitch = which ? p.pitch[l] : p.w;
+        const long long rows = which ? p.rows[l] : static_cast<long long>(p.h) * p.w;
+        __half* dst = (which ? p.dst_b[l] : p.dst_a) + static_cast<long long>(b) * rows * Kp;
+        const float(*t)[65] = (l == 0) ? t0 : (l == 1) ? t1 : (l == 2) ? t2 : t3;
+        const int v0 = y0 >> l, u0 = x0 >> l;
+        for (int i = tid; i < side * side * 32; i += 256) {
+            const int c = i >> 5, kk = 2 * (i & 31);
+            const int v = v0 + c / side, u = u0 + c % side;
+            if (v >= hl || u >= wl || k0 + kk >= p.D) continue;
+            const float f0 = t[c][kk], f1 = t[c][kk + 1];
+            const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+            __half* drow = dst + (static_cast<long long>(v) * pitch + u) * Kp + k0 + kk;
+            *reinterpret_cast<__half2*>(drow) = __halves2half2(h0, h1);
+            if (p.split) {
+                const float l0 = (f0 - __half2float(h0)) * 2048.f, l1 = (f1 - __half2float(h1)) * 2048.f;
+                const __half2 lo = __halves2half2(__float2half_rn(l0), __float2half_rn(l1));
+                const __half2 hs = __halves2half2(__float2half_rn(__half2float(h0) * (1.f / 2048.f)),
+                                                  __float2half_rn(__half2float(h1) * (1.f / 2048.f)));
+                *reinterpret_cast<__half2*>(drow + p.D) = which ? lo : hs;
+                *reinterpret_cast<__half2*>(drow + 2 * p.D) = which ? hs : lo;
+            }
+        }
+        // zero operand rows at the pad columns u in [wl, pitch): written by the last block column
+        if (which && pitch != wl && bxi == p.bx - 1) {
+            const int npad = pitch - wl, parts = p.split ? 3 : 1;
+            for (int i = tid; i < side * npad * 32 * parts; i += 256) {
+                const int kk = 2 * (i & 31);
+                int r = i >> 5;
+                const int part = r % parts; r /= parts;
+                const int v = v0 + r / npad, u = wl + r % npad;
+                if (v >= hl || k0 + kk >= p.D) continue;
+                *reinterpret_cast<__half2*>(dst + (static_cast<long long>(v) * pitch + u) * Kp + part * p.D + k0 + kk) =
+                    __floats2half2_rn(0.f, 0.f);
+            }
         }
     }
 }
@@ -191,10 +225,10 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
     return SF_OK;
 }
 
-int launch_corr_pack(const PackParams& p, int total_tiles, int64_t B, cudaStream_t s) {
-    dim3 grid(total_tiles, (p.D + 63) / 64, static_cast<unsigned>(B));
+int launch_corr_pack(const PackParams& p, int64_t B, cudaStream_t s) {
+    dim3 grid(p.bx * p.by, (p.D + 63) / 64, static_cast<unsigned>(2 * B));
     prof_before(SF_KERNEL_CORR_PACK, s);
-    corr_pack_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
+    corr_pack_kernel<<<grid, 256, 0, s>>>(p);
     prof_after(SF_KERNEL_CORR_PACK, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

@@ -74,26 +74,20 @@ struct LookupParams {
 int launch_corr_lookup(const LookupParams& p, int groups, cudaStream_t s);
 
 // ------------------------------------------------------------- operand packing (corr_pack.cu)
-struct PackSeg {
-    const float* src;            // [B, D, h, w] with element strides sb, sk, sy, sx
-    long long sb, sk, sy, sx;
-    __half* dst;                 // [B, rows, Kp] fp16, K contiguous
-    int hl, wl, pitch, level;    // geometry of the (pooled) target grid; row m = v * pitch + u
-    int rows;                    // hl * pitch
-    int tile0;                   // first 32-row tile of this segment in blockIdx.x space
-    int amax_slot;               // which absmax slot scales this tensor
-    int is_b;                    // split layout: A = [hi | hi*2^-11 | lo*2^11], B = [hi | lo*2^11 | hi*2^-11]
-};
 struct PackParams {
-    PackSeg seg[1 + SF_NUM_LEVELS];
-    int nseg;
-    int D;                       // channels
-    int split;                   // 0: Kp = D, 1: Kp = 3*D
-    const unsigned* amax_bits;   // [2]
+    const float* src[2];                 // fmap1 (-> A), fmap2 (-> B levels): [B, D, h, w], element strides below
+    long long sb[2], sk[2], sy[2], sx[2];
+    __half* dst_a;                       // [B, N, Kp] fp16, K contiguous
+    __half* dst_b[SF_NUM_LEVELS];        // [B, h_l * pitch_l, Kp]; row m = v * pitch_l + u
+    int h, w, D, split;                  // split: Kp = 3 * D with A = [hi | hi*2^-11 | lo*2^11],
+                                         //                        B = [hi | lo*2^11 | hi*2^-11]
+    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS], rows[SF_NUM_LEVELS];
+    int bx, by;                          // 8x8 source-pixel blocks per image
+    const unsigned* amax_bits;           // [2] absmax of fmap1, fmap2
 };
 int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
                    const int64_t s1[4], const int64_t s2[4], unsigned* amax_bits, cudaStream_t s);
-int launch_corr_pack(const PackParams& p, int total_tiles, int64_t B, cudaStream_t s);
+int launch_corr_pack(const PackParams& p, int64_t B, cudaStream_t s);
 
 // --------------------------------------------------------- strict fp32 path (corr_simt.cu)
 int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
