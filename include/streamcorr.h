@@ -79,10 +79,13 @@ SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
 
 /* ---- correlation pyramid -------------------------------------------------------------------------
- * Level l of the pyramid is a dense matrix [B*N, h_l * pitch_l] fp32 (N = h*w): row b*N + y*w + x is the
- * h_l x w_l correlation image of query (b,y,x), rows padded to pitch_l = round_up(w_l, 4) floats with
- * zeros.  h_l = h >> l, w_l = w >> l (avg_pool2d(2,2) floor mode, core/corr.py:19-21).                */
-SF_API void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* pitch_l);
+ * Level l of the pyramid is a dense matrix [B*N, tiles_y * tiles_x * 16] fp32 (N = h*w): row b*N + y*w + x is the
+ * h_l x w_l correlation image of query (b,y,x), stored as 4x4 tiles (64 bytes each, tile-row-major; cell (v,u) at
+ * ((v/4)*tiles_x + u/4)*16 + (v%4)*4 + u%4; cells past h_l / w_l are zero) so that the lookup's 10x10 window
+ * touches few 64-byte blocks.  h_l = h >> l, w_l = w >> l (avg_pool2d(2,2) floor mode, core/corr.py:19-21),
+ * tiles = ceil(./4).                                                                                      */
+SF_API void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* tiles_y,
+                        int64_t* tiles_x);
 SF_API int64_t sf_corr_workspace_bytes(int64_t B, int64_t D, int64_t h, int64_t w, int precision);
 
 /* fmap1/fmap2: [B, D, h, w] fp32 with arbitrary element strides {sB, sD, sh, sw} (the model passes

@@ -53,7 +53,7 @@ def lib() -> ctypes.CDLL:
     L.sf_launch_count.restype = c_int64
     L.sf_profile_kernel.argtypes = [c_int, c_void_p, c_void_p]
     L.sf_profile_kernel.restype = None
-    L.sf_corr_level_dims.argtypes = [c_int64, c_int64, c_int, i64p, i64p, i64p]
+    L.sf_corr_level_dims.argtypes = [c_int64, c_int64, c_int, i64p, i64p, i64p, i64p]
     L.sf_corr_level_dims.restype = None
     L.sf_corr_workspace_bytes.argtypes = [c_int64, c_int64, c_int64, c_int64, c_int]
     L.sf_corr_workspace_bytes.restype = c_int64
@@ -89,9 +89,10 @@ def check(rc: int, what: str) -> None:
 
 
 def level_dims(h: int, w: int, level: int):
-    a, b, c = c_int64(), c_int64(), c_int64()
-    lib().sf_corr_level_dims(h, w, level, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-    return a.value, b.value, c.value
+    """(h_l, w_l, tiles_y, tiles_x) of pyramid level `level`; a query image holds tiles_y*tiles_x*16 floats."""
+    a, b, c, d = c_int64(), c_int64(), c_int64(), c_int64()
+    lib().sf_corr_level_dims(h, w, level, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d))
+    return a.value, b.value, c.value, d.value
 
 
 def i64_array(values):

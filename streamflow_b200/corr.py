@@ -7,9 +7,10 @@ Same public surface as the reference (``core/corr.py:6-54``):
     CorrBlock.corr(fmap1, fmap2) -> Tensor[B, h, w, 1, h, w]
     attributes: num_levels, radius, corr_pyramid (list of [B*N, 1, h_l, w_l] tensors)
 
-Differences that are invisible to the callers (``core/models/*.py``): the pyramid levels are row-padded
-strided views (row pitch rounded up to 4 floats) and every call only enqueues kernels on the current CUDA
-stream -- no host synchronisation (the reference does 4 CPU->GPU copies per lookup, core/corr.py:33).
+Differences that are invisible to the callers (``core/models/*.py``): the pyramid levels live in a 4x4-tiled
+layout (``include/streamcorr.h``) -- ``corr_pyramid`` materialises reference-shaped copies on first access,
+nothing on the hot path reads it -- and every call only enqueues kernels on the current CUDA stream, with no host
+synchronisation (the reference does 4 CPU->GPU copies per lookup, core/corr.py:33).
 """
 from __future__ import annotations
 
@@ -31,6 +32,34 @@ def _aligned_workspace(nbytes: int, device) -> tuple[torch.Tensor, int]:
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` costs ~10 us per call; skip it when `dev` is already current."""
+
+    __slots__ = ("_ctx",)
+
+    def __init__(self, dev):
+        self._ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+_DIMS_CACHE: dict = {}
+
+
+def _level_dims(h: int, w: int):
+    key = (h, w)
+    if key not in _DIMS_CACHE:
+        _DIMS_CACHE[key] = [_lib.level_dims(h, w, l) for l in range(_lib.NUM_LEVELS)]
+    return _DIMS_CACHE[key]
 
 
 class CorrBlock:
@@ -57,10 +86,10 @@ class CorrBlock:
         self._shape = (B, D, h, w)
         dev = f1.device
         L = _lib.lib()
-        self._dims = [_lib.level_dims(h, w, l) for l in range(num_levels)]
-        with torch.cuda.device(dev):
-            self._levels = [torch.empty((B * h * w, hl * pitch), dtype=torch.float32, device=dev)
-                            for (hl, wl, pitch) in self._dims]
+        self._dims = _level_dims(h, w)
+        with _on_device(dev):
+            self._levels = [torch.empty((B * h * w, th * tw * 16), dtype=torch.float32, device=dev)
+                            for (hl, wl, th, tw) in self._dims]
             ws_bytes = L.sf_corr_workspace_bytes(B, D, h, w, _lib.PRECISIONS[prec])
             ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
             rc = L.sf_corr_build(f1.data_ptr(), f2.data_ptr(), B, D, h, w, _lib.i64_array(f1.stride()),
@@ -68,11 +97,19 @@ class CorrBlock:
                                  ws_ptr, ws_bytes, _lib.PRECISIONS[prec], _stream_ptr(dev))
         _lib.check(rc, "sf_corr_build")
         del ws_buf
-        self.corr_pyramid = [
-            t.as_strided((B * h * w, 1, hl, wl), (hl * pitch, hl * pitch, pitch, 1))
-            for t, (hl, wl, pitch) in zip(self._levels, self._dims)
-        ]
+        self._pyramid_cache = None
         self._level_ptrs = _lib.ptr_array([t.data_ptr() for t in self._levels])
+
+    @property
+    def corr_pyramid(self):
+        """Reference-shaped pyramid: list of [B*N, 1, h_l, w_l] fp32 tensors (un-tiled copies, built lazily)."""
+        if self._pyramid_cache is None:
+            out = []
+            for t, (hl, wl, th, tw) in zip(self._levels, self._dims):
+                img = t.view(-1, th, tw, 4, 4).permute(0, 1, 3, 2, 4).reshape(-1, th * 4, tw * 4)
+                out.append(img[:, None, :hl, :wl].contiguous())
+            self._pyramid_cache = out
+        return self._pyramid_cache
 
     def __call__(self, coords):
         B, D, h, w = self._shape
@@ -85,7 +122,7 @@ class CorrBlock:
         if c.dtype != torch.float32 or not c.is_contiguous():
             c = c.float().contiguous()
         side = 2 * self.radius + 1
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             out = torch.empty((B, self.num_levels * side * side, h, w), dtype=torch.float32, device=dev)
             rc = _lib.lib().sf_corr_lookup(self._level_ptrs, c.data_ptr(), out.data_ptr(), B, h, w, self.radius,
                                            self.num_levels, _stream_ptr(dev))
@@ -102,18 +139,16 @@ class CorrBlock:
             raise StreamCorrError("from_dense_pyramid: need 4 levels, radius 4")
         BN, _, h, w = levels[0].shape
         self._shape = (1, 0, h, w) if BN == h * w else (BN // (h * w), 0, h, w)
-        self._dims = [_lib.level_dims(h, w, l) for l in range(self.num_levels)]
+        self._dims = _level_dims(h, w)
         self._levels = []
-        for lv, (hl, wl, pitch) in zip(levels, self._dims):
+        for lv, (hl, wl, th, tw) in zip(levels, self._dims):
             if tuple(lv.shape) != (BN, 1, hl, wl):
                 raise StreamCorrError(f"level shape {tuple(lv.shape)} != {(BN, 1, hl, wl)}")
-            buf = torch.zeros((BN, hl * pitch), dtype=torch.float32, device=lv.device)
-            buf.view(BN, hl, pitch)[:, :, :wl] = lv[:, 0].float()
+            pad = torch.zeros((BN, th * 4, tw * 4), dtype=torch.float32, device=lv.device)
+            pad[:, :hl, :wl] = lv[:, 0].float()
+            buf = pad.view(BN, th, 4, tw, 4).permute(0, 1, 3, 2, 4).reshape(BN, th * tw * 16).contiguous()
             self._levels.append(buf)
-        self.corr_pyramid = [
-            t.as_strided((BN, 1, hl, wl), (hl * pitch, hl * pitch, pitch, 1))
-            for t, (hl, wl, pitch) in zip(self._levels, self._dims)
-        ]
+        self._pyramid_cache = None
         self._level_ptrs = _lib.ptr_array([t.data_ptr() for t in self._levels])
         return self
 
@@ -158,21 +193,25 @@ class CorrGroup:
                 raise StreamCorrError(f"coords must be [{B}, 2, {h}, {w}], got {tuple(c.shape)}")
             c = c.detach()
             cs.append(c if (c.dtype == torch.float32 and c.is_contiguous()) else c.float().contiguous())
-        with torch.cuda.device(dev):
+        L = _lib.lib()
+        code = _lib.torch_dtype_code(self.out_dtype)
+        with _on_device(dev):
             out = torch.empty((B, G, 324, h, w), dtype=self.out_dtype, device=dev)
+            base, per = out.data_ptr(), 324 * h * w * out.element_size()
+            stream = _stream_ptr(dev)
             if B == 1:
-                outs = [out[0, g].data_ptr() for g in range(G)]
-                rc = _lib.lib().sf_corr_lookup_group(
-                    G, self._level_ptrs, _lib.ptr_array([c.data_ptr() for c in cs]), _lib.ptr_array(outs),
-                    _lib.torch_dtype_code(self.out_dtype), B, h, w, 4, 4, _stream_ptr(dev))
+                rc = L.sf_corr_lookup_group(G, self._level_ptrs, _lib.ptr_array([c.data_ptr() for c in cs]),
+                                            _lib.ptr_array([base + g * per for g in range(G)]), code, 1, h, w, 4,
+                                            4, stream)
                 _lib.check(rc, "sf_corr_lookup_group")
             else:   # batch-strided destination: one launch per batch element keeps the (B T) row order
+                img = [th * tw * 16 * 4 for (hl, wl, th, tw) in blocks[0]._dims]
                 for b in range(B):
-                    lv = _lib.ptr_array([t[b * h * w:].data_ptr() for blk in blocks for t in blk._levels])
-                    outs = [out[b, g].data_ptr() for g in range(G)]
-                    rc = _lib.lib().sf_corr_lookup_group(
-                        G, lv, _lib.ptr_array([c[b].data_ptr() for c in cs]), _lib.ptr_array(outs),
-                        _lib.torch_dtype_code(self.out_dtype), 1, h, w, 4, 4, _stream_ptr(dev))
+                    lv = _lib.ptr_array([t.data_ptr() + b * h * w * img[l]
+                                         for blk in blocks for l, t in enumerate(blk._levels)])
+                    rc = L.sf_corr_lookup_group(G, lv, _lib.ptr_array([c.data_ptr() + b * 2 * h * w * 4 for c in cs]),
+                                                _lib.ptr_array([base + (b * G + g) * per for g in range(G)]), code,
+                                                1, h, w, 4, 4, stream)
                     _lib.check(rc, "sf_corr_lookup_group")
         return out.view(B * G, 324, h, w)
 

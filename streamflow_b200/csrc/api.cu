@@ -36,8 +36,9 @@ LevelGeom make_level_geom(int64_t h, int64_t w) {
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         g.h[l] = static_cast<int>(h >> l);
         g.w[l] = static_cast<int>(w >> l);
-        g.pitch[l] = (g.w[l] + 3) & ~3;
-        g.img[l] = static_cast<long long>(g.h[l]) * g.pitch[l];
+        g.th[l] = (g.h[l] + 3) >> 2;
+        g.tw[l] = (g.w[l] + 3) >> 2;
+        g.img[l] = static_cast<long long>(g.th[l]) * g.tw[l] * 16;
     }
     return g;
 }
@@ -193,11 +194,13 @@ int sf_device_ok(void) {
     return query_device(&di);
 }
 
-void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* pitch_l) {
+void sf_corr_level_dims(int64_t h, int64_t w, int level, int64_t* h_l, int64_t* w_l, int64_t* tiles_y,
+                        int64_t* tiles_x) {
     const int64_t hl = h >> level, wl = w >> level;
     if (h_l) *h_l = hl;
     if (w_l) *w_l = wl;
-    if (pitch_l) *pitch_l = (wl + 3) & ~int64_t(3);
+    if (tiles_y) *tiles_y = (hl + 3) >> 2;
+    if (tiles_x) *tiles_x = (wl + 3) >> 2;
 }
 
 int64_t sf_corr_workspace_bytes(int64_t B, int64_t D, int64_t h, int64_t w, int precision) {
@@ -249,10 +252,12 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     pp.split = (precision == SF_PREC_F16X2);
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         pp.dst_b[l] = reinterpret_cast<__half*>(wsb + ws.b_off[l]);
-        pp.hl[l] = g.h[l]; pp.wl[l] = g.w[l]; pp.pitch[l] = g.pitch[l]; pp.rows[l] = (int)g.img[l];
+        pp.hl[l] = g.h[l]; pp.wl[l] = g.w[l]; pp.th[l] = g.th[l]; pp.tw[l] = g.tw[l]; pp.rows[l] = (int)g.img[l];
     }
     pp.bx = (int)((w + 7) / 8); pp.by = (int)((h + 7) / 8);
     pp.amax_bits = amax;
+    // tile-grid cells of levels 2-3 can lie outside every 8x8 source block: clear those (small) operands first
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.b_off[2], 0, ws.total - ws.b_off[2], s));
     if (int rc = launch_corr_pack(pp, B, s)) return rc;
 
     CorrGemmParams gp{};
@@ -310,7 +315,7 @@ static int lookup_common(int G, const float* const* levels, const float* const* 
         p.out[gi] = out[gi];
     }
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
-        p.hl[l] = g.h[l]; p.wl[l] = g.w[l]; p.pitch[l] = g.pitch[l]; p.img[l] = g.img[l];
+        p.hl[l] = g.h[l]; p.wl[l] = g.w[l]; p.th[l] = g.th[l]; p.tw[l] = g.tw[l]; p.img[l] = g.img[l];
     }
     p.N = (int)(h * w);
     p.BN = B * h * w;

@@ -4,12 +4,15 @@
 // HBM-bound gather.  Algorithmic bytes per query: 4 levels x 10x10 fp32 window (1600 B) + 8 B coords
 // + 4 x 81 fp32 outputs (1296 B) = 2904 B.
 //
+// Each query's correlation image is stored as 4x4 tiles of 64 B (see sf_internal.h): a 10x10 window at an
+// arbitrary offset touches on average 3.25 x 3.25 tiles = 676 B of 64-byte DRAM fetches, against 1024 B for a
+// row-major image (10 rows x 1.6 blocks; measured 87.7 MB of DRAM reads for 33.8 MB of window bytes).
+//
 // Mapping: one CTA = 32 consecutive queries x ONE pyramid level (grid = tiles x 4 levels x groups).
 //   phase 0  warp 0, lane = query: coords -> integer window origin (x0, y0) and the single fractional
 //            pair (ax, ay) shared by all 81 taps of the level (window offsets are integers);
-//   phase 1  all 128 threads, thread = (query, 16-byte chunk): each of the 10 window rows is fetched as
-//            3-4 aligned 128-bit chunks with cp.async.cg (zero-filled outside the image), so the four
-//            lanes of a query read 48-64 contiguous bytes per row and every thread has 10 loads in flight;
+//   phase 1  all 128 threads, thread = (query, tile column): the up-to 4x4 tiles under the window are fetched as
+//            16-byte cp.async.cg chunks (zero-filled outside the image), up to 13 loads in flight per thread;
 //   phase 2  lane = query: conflict-free LDS.128 of its own rows, horizontal then vertical lerp in
 //            registers, and one 128-byte coalesced store per output channel straight into the NCHW result
 //            (channel = l*81 + i*9 + j, i moves x, j moves y).  Warps split the 9 y-offsets.
@@ -20,9 +23,10 @@ namespace sf {
 namespace {
 
 constexpr int kQ = 32;              // queries per CTA
-constexpr int kRowFloats = 16;      // 4 chunks of 4 floats per window row
+constexpr int kRowFloats = 16;      // 4 tile columns of 4 floats per staged row
 constexpr int kRows = 2 * SF_RADIUS + 2;                 // 10 window rows / columns
-constexpr int kWinStride = kRows * kRowFloats + 4;       // 164 floats: == 4 (mod 32) -> LDS.128 conflict-free
+constexpr int kStageRows = kRows + 3;                    // window may start at row 0..3 of its first tile
+constexpr int kWinStride = kStageRows * kRowFloats + 4;  // 212 floats: 8 consecutive queries -> distinct bank quads
 constexpr int kSide = 2 * SF_RADIUS + 1;                 // 9
 
 __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool pred) {
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     const int grp = blockIdx.z;
     const long long q0 = static_cast<long long>(blockIdx.x) * kQ;
 
-    const int hl = p.hl[lvl], wl = p.wl[lvl], pitch = p.pitch[lvl];
+    const int hl = p.hl[lvl], wl = p.wl[lvl], th = p.th[lvl], tw = p.tw[lvl];
 
     if (warp == 0) {
         const long long qid = q0 + lane;
@@ -69,23 +73,23 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    {   // phase 1: thread = (query, chunk)
-        const int q = tid >> 2, ch = tid & 3;
+    {   // phase 1: thread = (query, tile column)
+        const int q = tid >> 2, j = tid & 3;
         const long long qid = q0 + q;
         const int x0 = s_x0[q], y0 = s_y0[q];
-        const int a = x0 & ~3;                  // 16-byte aligned column of the first chunk
-        const int o = x0 - a;                   // 0..3
-        if (qid < p.BN && (ch < 3 || o == 3)) { // 4th chunk only holds tap 12 (= o + 9 with o == 3)
-            const int col = a + 4 * ch;
-            const bool colok = (col >= 0) && (col + 4 <= pitch);
+        const int ox = x0 & 3, oy = y0 & 3;                 // window origin inside its first tile
+        const int txc = (x0 >> 2) + j, ty0 = y0 >> 2;
+        if (qid < p.BN && 4 * j < ox + kRows) {             // tile column j overlaps window columns ox .. ox+9
+            const bool colok = (txc >= 0) && (txc < tw);
             const float* base = p.lvl[grp][lvl] + qid * p.img[lvl];
-            float* dst = win + q * kWinStride + ch * 4;
+            float* dst = win + q * kWinStride + j * 4;
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                const int y = y0 + r;
-                const bool ok = colok && (y >= 0) && (y < hl);
-                const float* src = ok ? base + static_cast<long long>(y) * pitch + col : base;
-                cp_async16_zfill(dst + r * kRowFloats, src, ok);
+            for (int R = 0; R < kStageRows; ++R) {          // staged row R = tile row R>>2, row R&3 inside the tile
+                if (R < oy || R >= oy + kRows) continue;    // outside the window (still in the same 64 B block)
+                const int ty = ty0 + (R >> 2);
+                const bool ok = colok && (ty >= 0) && (ty < th);
+                const float* src = ok ? base + ((static_cast<long long>(ty) * tw + txc) << 4) + ((R & 3) << 2) : base;
+                cp_async16_zfill(dst + R * kRowFloats, src, ok);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     const int je = (warp == 0) ? 2 : (2 * warp + 2);       // 2,4,6,8
     const float ax = s_ax[lane], ay = s_ay[lane];
     const int o = s_x0[lane] & 3;
-    const float4* wq = reinterpret_cast<const float4*>(win + lane * kWinStride);
+    const float4* wq = reinterpret_cast<const float4*>(win + lane * kWinStride) + (s_y0[lane] & 3) * 4;
 
     const long long b = qid / p.N;
     const long long n = qid - b * p.N;

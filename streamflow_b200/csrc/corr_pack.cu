@@ -4,7 +4,7 @@
 //  corr_pack_kernel reads the fp32 feature maps through their ORIGINAL strides (the model hands over
 //                   channels-last views, core/models/streamflow.py:107,110) and writes K-major fp16 operand
 //                   matrices the TMA can tile:  A = fmap1 as [B, N, Kp];  B_l = avg-pooled fmap2 at level l
-//                   as [B, h_l*pitch_l, Kp] (rows at pad columns are zero).  Pooling the operand instead of
+//                   as [B, th_l*tw_l*16, Kp] in 4x4-tiled cell order (pad cells are zero rows).  Pooling the operand instead of
 //                   the volume uses linearity: avg_pool(f1^T f2) == f1^T avg_pool(f2) (core/corr.py:19-21).
 //                   With split != 0 each value is stored as hi/lo fp16 parts concatenated along K so that one
 //                   GEMM over Kp = 3*D accumulates  hi*hi + hi*lo + lo*hi  (fp32-faithful mode).
@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     for (int l = 0; l < nlev; ++l) {
         const int side = 8 >> l;                                   // cells per block edge at this level
         const int hl = which ? p.hl[l] : p.h, wl = which ? p.wl[l] : p.w;
-        const int pitch = which ? p.pitch[l] : p.w;
+        // A rows are the dense query index y*w + x; B rows follow the 4x4-tiled image layout of the pyramid
+        // (the GEMM's column index IS the offset inside the query's correlation image), pad cells = zero rows
+        const int vmax = which ? p.th[l] * 4 : p.h, umax = which ? p.tw[l] * 4 : p.w;
         const long long rows = which ? p.rows[l] : static_cast<long long>(p.h) * p.w;
         __half* dst = (which ? p.dst_b[l] : p.dst_a) + static_cast<long long>(b) * rows * Kp;
         const float(*t)[65] = (l == 0) ? t0 : (l == 1) ? t1 : (l == 2) ? t2 : t3;
@@ -162,10 +164,12 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
         for (int i = tid; i < side * side * 32; i += 256) {
             const int c = i >> 5, kk = 2 * (i & 31);
             const int v = v0 + c / side, u = u0 + c % side;
-            if (v >= hl || u >= wl || k0 + kk >= p.D) continue;
-            const float f0 = t[c][kk], f1 = t[c][kk + 1];
+            if (v >= vmax || u >= umax || k0 + kk >= p.D) continue;
+            const bool valid = (v < hl) && (u < wl);
+            const float f0 = valid ? t[c][kk] : 0.f, f1 = valid ? t[c][kk + 1] : 0.f;
             const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-            __half* drow = dst + (static_cast<long long>(v) * pitch + u) * Kp + k0 + kk;
+            const long long m = which ? tiled_offset(v, u, p.tw[l]) : static_cast<long long>(v) * p.w + u;
+            __half* drow = dst + m * Kp + k0 + kk;
             *reinterpret_cast<__half2*>(drow) = __halves2half2(h0, h1);
             if (p.split) {
                 const float l0 = (f0 - __half2float(h0)) * 2048.f, l1 = (f1 - __half2float(h1)) * 2048.f;
@@ -174,19 +178,6 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
                                                   __float2half_rn(__half2float(h1) * (1.f / 2048.f)));
                 *reinterpret_cast<__half2*>(drow + p.D) = which ? lo : hs;
                 *reinterpret_cast<__half2*>(drow + 2 * p.D) = which ? hs : lo;
-            }
-        }
-        // zero operand rows at the pad columns u in [wl, pitch): written by the last block column
-        if (which && pitch != wl && bxi == p.bx - 1) {
-            const int npad = pitch - wl, parts = p.split ? 3 : 1;
-            for (int i = tid; i < side * npad * 32 * parts; i += 256) {
-                const int kk = 2 * (i & 31);
-                int r = i >> 5;
-                const int part = r % parts; r /= parts;
-                const int v = v0 + r / npad, u = wl + r % npad;
-                if (v >= hl || k0 + kk >= p.D) continue;
-                *reinterpret_cast<__half2*>(dst + (static_cast<long long>(v) * pitch + u) * Kp + part * p.D + k0 + kk) =
-                    __floats2half2_rn(0.f, 0.f);
             }
         }
     }

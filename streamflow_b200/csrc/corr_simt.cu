@@ -23,9 +23,9 @@ __global__ void gather_dense_kernel(const float* __restrict__ src, long long sb,
 
 constexpr int TM = 64, TN = 64, TK = 16;
 
-// C[n, m] = alpha * sum_k A[k, n] * Bm[k, m];  A, Bm dense [D, N];  C row n has h rows of `pitch` floats.
+// C[n, m] = sum_k A[k, n] * Bm[k, m] / alpha;  A, Bm dense [D, N];  C row n is a 4x4-tiled image (tw tiles per row).
 __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
-                                                       float* __restrict__ C, int D, int N, int w, int pitch,
+                                                       float* __restrict__ C, int D, int N, int w, int tw,
                                                        long long img, float alpha) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
@@ -67,24 +67,26 @@ __global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__
             const int m = m0 + tx * 4 + j;
             if (m >= N) continue;
             const int v = m / w, u = m - v * w;
-            C[static_cast<long long>(n) * img + static_cast<long long>(v) * pitch + u] = acc[i][j] / alpha;
+            C[static_cast<long long>(n) * img + tiled_offset(v, u, tw)] = acc[i][j] / alpha;
         }
     }
 }
 
-// level l -> level l+1, one thread per output element including the zero pad columns
-__global__ void pool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int pitch_s, long long img_s,
-                               int ho, int wo, int pitch_o, long long img_o, long long rows) {
+// level l -> level l+1 (both 4x4-tiled), one thread per output cell of the tile grid; pad cells are written as 0
+__global__ void pool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, int tw_s, long long img_s,
+                               int ho, int wo, int tw_o, long long img_o, long long rows) {
     const long long total = rows * img_o;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / img_o;
         const int rem = static_cast<int>(i - r * img_o);
-        const int v = rem / pitch_o, u = rem - v * pitch_o;
+        const int tile = rem >> 4, in = rem & 15;
+        const int v = (tile / tw_o) * 4 + (in >> 2), u = (tile % tw_o) * 4 + (in & 3);
         float out = 0.f;
         if (u < wo && v < ho) {
-            const float* s = src + r * img_s + static_cast<long long>(2 * v) * pitch_s + 2 * u;
-            out = (((s[0] + s[1]) + s[pitch_s]) + s[pitch_s + 1]) * 0.25f;
+            const float* s = src + r * img_s;
+            out = (((s[tiled_offset(2 * v, 2 * u, tw_s)] + s[tiled_offset(2 * v, 2 * u + 1, tw_s)]) +
+                    s[tiled_offset(2 * v + 1, 2 * u, tw_s)]) + s[tiled_offset(2 * v + 1, 2 * u + 1, tw_s)]) * 0.25f;
         }
         dst[i] = out;
     }
@@ -102,16 +104,16 @@ int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int
     prof_before(0, s); prof_before(0, s); prof_before(0, s); prof_before(0, s); prof_before(0, s);   // 6 launches
     gather_dense_kernel<<<gb, 256, 0, s>>>(f1, s1[0], s1[1], s1[2], s1[3], ws_a, (int)D, (int)h, (int)w, total);
     gather_dense_kernel<<<gb, 256, 0, s>>>(f2, s2[0], s2[1], s2[2], s2[3], ws_b, (int)D, (int)h, (int)w, total);
-    if (g.pitch[0] != g.w[0])
+    if ((g.h[0] & 3) || (g.w[0] & 3))
         SF_CUDA_CHECK(cudaMemsetAsync(levels[0], 0, sizeof(float) * B * N * g.img[0], s));
     dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((N + TM - 1) / TM), (unsigned)B);
-    sgemm_tn_kernel<<<grid, 256, 0, s>>>(ws_a, ws_b, levels[0], (int)D, (int)N, (int)w, g.pitch[0], g.img[0],
+    sgemm_tn_kernel<<<grid, 256, 0, s>>>(ws_a, ws_b, levels[0], (int)D, (int)N, (int)w, g.tw[0], g.img[0],
                                          sqrtf(static_cast<float>(D)));
     for (int l = 0; l + 1 < SF_NUM_LEVELS; ++l) {
         const long long rows = B * N, tot = rows * g.img[l + 1];
         const int pb = static_cast<int>(std::min<long long>((tot + 255) / 256, 148 * 32));
-        pool2x2_kernel<<<pb, 256, 0, s>>>(levels[l], levels[l + 1], g.pitch[l], g.img[l], g.h[l + 1], g.w[l + 1],
-                                          g.pitch[l + 1], g.img[l + 1], rows);
+        pool2x2_kernel<<<pb, 256, 0, s>>>(levels[l], levels[l + 1], g.tw[l], g.img[l], g.h[l + 1], g.w[l + 1],
+                                          g.tw[l + 1], g.img[l + 1], rows);
     }
     prof_after(SF_KERNEL_CORR_SIMT, s);
     SF_CUDA_CHECK(cudaGetLastError());

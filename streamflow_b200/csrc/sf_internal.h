@@ -33,10 +33,17 @@ void set_error(const char* fmt, ...);
 void prof_before(int kind, cudaStream_t s);
 void prof_after(int kind, cudaStream_t s);
 
+// Per-query correlation images are stored as 4x4 tiles (64 B each, tile-row-major): the lookup's 10x10 window then
+// touches ~3.25 x 3.25 sixty-four-byte blocks instead of 10 rows x 1.6 blocks of a row-major image.
 struct LevelGeom {
-    int h[SF_NUM_LEVELS], w[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS];
-    long long img[SF_NUM_LEVELS];   // floats per query image = h_l * pitch_l
+    int h[SF_NUM_LEVELS], w[SF_NUM_LEVELS];       // valid cells
+    int th[SF_NUM_LEVELS], tw[SF_NUM_LEVELS];     // tiles: ceil(h_l / 4), ceil(w_l / 4)
+    long long img[SF_NUM_LEVELS];                 // floats per query image = th * tw * 16 (cells past h_l, w_l are 0)
 };
+// offset of cell (v, u) inside a tiled image with `tw` tiles per row
+__host__ __device__ inline int tiled_offset(int v, int u, int tw) {
+    return (((v >> 2) * tw + (u >> 2)) << 4) + ((v & 3) << 2) + (u & 3);
+}
 LevelGeom make_level_geom(int64_t h, int64_t w);
 
 struct DeviceInfo {
@@ -65,7 +72,7 @@ struct LookupParams {
     const float* lvl[SF_MAX_GROUPS][SF_NUM_LEVELS];
     const float* coords[SF_MAX_GROUPS];
     void* out[SF_MAX_GROUPS];
-    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS];
+    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], th[SF_NUM_LEVELS], tw[SF_NUM_LEVELS];
     long long img[SF_NUM_LEVELS];
     int N;            // h * w
     long long BN;     // queries per group
@@ -78,10 +85,10 @@ struct PackParams {
     const float* src[2];                 // fmap1 (-> A), fmap2 (-> B levels): [B, D, h, w], element strides below
     long long sb[2], sk[2], sy[2], sx[2];
     __half* dst_a;                       // [B, N, Kp] fp16, K contiguous
-    __half* dst_b[SF_NUM_LEVELS];        // [B, h_l * pitch_l, Kp]; row m = v * pitch_l + u
+    __half* dst_b[SF_NUM_LEVELS];        // [B, th_l*tw_l*16, Kp]; row m = tiled_offset(v, u, tw_l)
     int h, w, D, split;                  // split: Kp = 3 * D with A = [hi | hi*2^-11 | lo*2^11],
                                          //                        B = [hi | lo*2^11 | hi*2^-11]
-    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], pitch[SF_NUM_LEVELS], rows[SF_NUM_LEVELS];
+    int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], th[SF_NUM_LEVELS], tw[SF_NUM_LEVELS], rows[SF_NUM_LEVELS];
     int bx, by;                          // 8x8 source-pixel blocks per image
     const unsigned* amax_bits;           // [2] absmax of fmap1, fmap2
 };

@@ -21,7 +21,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import StreamCorrError
-from .corr import _aligned_workspace, _stream_ptr
+from .corr import _aligned_workspace, _on_device, _stream_ptr
 
 
 class AttentionHandle:
@@ -52,6 +52,20 @@ class AttentionHandle:
         npad = self.E.numel() // (P * mt * 128)
         e = self.E.view(P, mt, npad // 64, 128, 64).float().sum(-1).sum(2)       # [P, mt, 128]
         return e.reshape(P, mt * 128)[:, :N]
+
+
+def _weight_2d(module, attr, param, rows, cols):
+    """fp32 contiguous [rows, cols] view of a conv weight, cached until the parameter is modified in place or
+    replaced (keeps ~6 us of reshape/detach off every call)."""
+    key = (param.data_ptr(), param._version, param.dtype, param.device)
+    cached = getattr(module, attr, None)
+    if cached is None or cached[0] != key:
+        w = param.detach().reshape(rows, cols)
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        cached = (key, w)
+        object.__setattr__(module, attr, cached)
+    return cached[1]
 
 
 def _check_cfg(dim, heads, dim_head):
@@ -85,10 +99,8 @@ class Attention(nn.Module):
         N = h * w
         dev = x.device
         L = _lib.lib()
-        wq = self.to_qk.weight.detach().reshape(2 * self.dim_head, C)
-        if wq.dtype != torch.float32 or not wq.is_contiguous():
-            wq = wq.float().contiguous()
-        with torch.cuda.device(dev):
+        wq = _weight_2d(self, "_wq_cache", self.to_qk.weight, 2 * self.dim_head, C)
+        with _on_device(dev):
             npad = L.sf_gma_npad(N)
             E = torch.empty((L.sf_gma_e_elems(P, N),), dtype=torch.float16, device=dev)
             rowsum = torch.empty((P, N), dtype=torch.float32, device=dev)
@@ -129,13 +141,11 @@ class Aggregate(nn.Module):
             x = x.contiguous()
         P, C, h, w = x.shape
         dev = x.device
-        wv = self.to_v.weight.detach().reshape(self.dim_head, C)
-        if wv.dtype != torch.float32 or not wv.is_contiguous():
-            wv = wv.float().contiguous()
-        gamma = self.gamma.detach()
+        wv = _weight_2d(self, "_wv_cache", self.to_v.weight, self.dim_head, C)
+        gamma = self.gamma
         if gamma.dtype != torch.float32:
-            gamma = gamma.float()
-        with torch.cuda.device(dev):
+            gamma = gamma.detach().float()
+        with _on_device(dev):
             out = torch.empty((P, C, h, w), dtype=torch.float32, device=dev)
             rc = _lib.lib().sf_gma_aggregate(attn.E.data_ptr(), attn.rowsum.data_ptr(), x.data_ptr(),
                                              _lib.torch_dtype_code(x.dtype), wv.data_ptr(), gamma.data_ptr(),

@@ -47,10 +47,13 @@ def test_build_small_vs_reference(small, prec):
         assert got.shape == small[f"level{l}"].shape
         err = rel_err(got, small[f"level{l}"])
         assert err < TOL_BUILD[prec], f"{prec} level {l}: rel err {err:.3e}"
-    # pad columns of the row-padded storage are zero (the lookup relies on it)
-    for buf, (hl, wl, pitch) in zip(blk._levels, blk._dims):
-        if pitch != wl:
-            assert float(buf.view(-1, hl, pitch)[:, :, wl:].abs().max()) == 0.0
+    # pad cells of the 4x4-tiled storage are zero (the lookup relies on it)
+    for buf, (hl, wl, th, tw) in zip(blk._levels, blk._dims):
+        img = buf.view(-1, th, tw, 4, 4).permute(0, 1, 3, 2, 4).reshape(-1, th * 4, tw * 4)
+        if th * 4 != hl:
+            assert float(img[:, hl:, :].abs().max()) == 0.0
+        if tw * 4 != wl:
+            assert float(img[:, :, wl:].abs().max()) == 0.0
     out = blk(cuda(small["coords_jitter"]))
     assert rel_err(out.cpu().numpy(), small["lookup_jitter"]) < TOL_BUILD[prec]
 
