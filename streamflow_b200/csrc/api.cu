@@ -320,7 +320,7 @@ static int lookup_common(int G, const float* const* levels, const float* const* 
     p.N = (int)(h * w);
     p.BN = B * h * w;
     p.out_f16 = (out_dtype == SF_DT_F16);
-    return launch_corr_lookup(p, G, static_cast<cudaStream_t>(stream));
+    return launch_corr_lookup(p, G, di.sms, static_cast<cudaStream_t>(stream));
 }
 
 int sf_corr_lookup(const float* const levels[SF_NUM_LEVELS], const float* coords, float* out, int64_t B, int64_t h,

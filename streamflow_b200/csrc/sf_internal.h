@@ -77,8 +77,9 @@ struct LookupParams {
     int N;            // h * w
     long long BN;     // queries per group
     int out_f16;
+    long long tiles, items;   // filled by the launcher: 32-query tiles per group, tiles * groups * levels
 };
-int launch_corr_lookup(const LookupParams& p, int groups, cudaStream_t s);
+int launch_corr_lookup(const LookupParams& p, int groups, int num_sms, cudaStream_t s);
 
 // ------------------------------------------------------------- operand packing (corr_pack.cu)
 struct PackParams {
