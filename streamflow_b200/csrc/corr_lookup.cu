@@ -55,36 +55,36 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const long long items = p.items;
+    const int items = static_cast<int>(p.items), tiles = static_cast<int>(p.tiles), BN = static_cast<int>(p.BN);
 
-    // item -> (group, query tile, level); levels of one tile are adjacent items
-    auto decode = [&](long long it, int& grp, long long& q0, int& lvl) {
-        lvl = static_cast<int>(it & 3);
-        const long long t = it >> 2;
-        grp = static_cast<int>(t / p.tiles);
-        q0 = (t - grp * p.tiles) * kQ;
+    // item -> (group, query tile, level); levels of one tile are adjacent items.  All index math is 32-bit
+    // (the launcher checks the ranges): 64-bit multiplies/divides were half of the instruction stream.
+    auto decode = [&](int it, int& grp, int& q0, int& lvl) {
+        lvl = it & 3;
+        const unsigned t = static_cast<unsigned>(it) >> 2;
+        grp = static_cast<int>(t / static_cast<unsigned>(tiles));
+        q0 = static_cast<int>(t - static_cast<unsigned>(grp) * tiles) * kQ;
     };
     // stage A: warp 0 fetches the coordinates of an item into registers
-    auto load_coords = [&](long long it, float& cx, float& cy) {
+    auto load_coords = [&](int it, float& cx, float& cy) {
         cx = cy = -1e30f;
         if (it < items) {
-            int grp, lvl;
-            long long q0;
+            int grp, lvl, q0;
             decode(it, grp, q0, lvl);
-            const long long qid = q0 + lane;
-            if (qid < p.BN) {
-                const long long b = qid / p.N;
-                const long long n = qid - b * p.N;
-                const float* c = p.coords[grp] + b * 2 * p.N + n;
+            const int qid = q0 + lane;
+            if (qid < BN) {
+                const int b = static_cast<unsigned>(qid) / static_cast<unsigned>(p.N);
+                const int n = qid - b * p.N;
+                const float* c = p.coords[grp] + static_cast<long long>(b) * 2 * p.N + n;
                 cx = __ldg(c);
                 cy = __ldg(c + p.N);
             }
         }
     };
     // stage B1: warp 0 turns coordinates into the window origin + fractions of the item's level
-    auto write_meta = [&](long long it, int buf, float cx, float cy) {
+    auto write_meta = [&](int it, int buf, float cx, float cy) {
         if (it >= items) return;
-        const int lvl = static_cast<int>(it & 3);
+        const int lvl = it & 3;
         const float inv = 1.0f / static_cast<float>(1 << lvl);
         // Far outside the image every tap is zero; clamping keeps the int conversion defined
         // (NaN / missing coordinates clamp to the lower bound and yield zeros).
@@ -97,36 +97,39 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
         meta[buf].y0[lane] = static_cast<int>(yf);
     };
     // stage B2: all threads, thread = (query, tile column): issue the window's 16-byte chunks
-    auto issue_window = [&](long long it, int buf) {
+    auto issue_window = [&](int it, int buf) {
         if (it < items) {
-            int grp, lvl;
-            long long q0;
+            int grp, lvl, q0;
             decode(it, grp, q0, lvl);
             const int th = p.th[lvl], tw = p.tw[lvl];
             const int q = tid >> 2, j = tid & 3;
-            const long long qid = q0 + q;
+            const int qid = q0 + q;
             const int x0 = meta[buf].x0[q], y0 = meta[buf].y0[q];
             const int ox = x0 & 3, oy = y0 & 3;             // window origin inside its first tile
             const int txc = (x0 >> 2) + j, ty0 = y0 >> 2;
-            if (qid < p.BN && 4 * j < ox + kRows) {         // tile column j overlaps window columns ox .. ox+9
+            if (qid < BN && 4 * j < ox + kRows) {           // tile column j overlaps window columns ox .. ox+9
                 const bool colok = (txc >= 0) && (txc < tw);
-                const float* base = p.lvl[grp][lvl] + qid * p.img[lvl];
+                const float* base = p.lvl[grp][lvl] + static_cast<long long>(qid) * p.img[lvl];
                 float* dst = win0 + buf * (kQ * kWinStride) + q * kWinStride + j * 4;
 #pragma unroll
-                for (int R = 0; R < kStageRows; ++R) {      // staged row R = tile row R>>2, row R&3 inside the tile
-                    if (R < oy || R >= oy + kRows) continue;
-                    const int ty = ty0 + (R >> 2);
+                for (int tr = 0; tr < 4; ++tr) {            // tile row: one 64-bit address per 64-byte tile
+                    const int ty = ty0 + tr;
                     const bool ok = colok && (ty >= 0) && (ty < th);
-                    const float* src =
-                        ok ? base + ((static_cast<long long>(ty) * tw + txc) << 4) + ((R & 3) << 2) : base;
-                    cp_async16_zfill(dst + R * kRowFloats, src, ok);
+                    const float* tile = ok ? base + ((ty * tw + txc) << 4) : base;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {        // row inside the tile: constant offsets from here on
+                        const int R = tr * 4 + rr;
+                        if (R >= kStageRows) continue;
+                        if (R < oy || R >= oy + kRows) continue;   // outside the window (same 64 B block)
+                        cp_async16_zfill(dst + R * kRowFloats, ok ? tile + rr * 4 : tile, ok);
+                    }
                 }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const long long first = blockIdx.x, step = gridDim.x;
+    const int first = blockIdx.x, step = gridDim.x;
     float cx = 0.f, cy = 0.f;
     // prologue: item 0 fully staged, coordinates of item 1 in flight
     if (warp == 0) {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     issue_window(first, 0);
 
     int buf = 0;
-    for (long long it = first; it < items; it += step, buf ^= 1) {
+    for (int it = first; it < items; it += step, buf ^= 1) {
         if (warp == 0) {
             write_meta(it + step, buf ^ 1, cx, cy);
             load_coords(it + 2 * step, cx, cy);
@@ -149,20 +152,23 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
         __syncthreads();
 
         // stage C: lane = query; warp w owns y-offsets j in [jb, je]
-        int grp, lvl;
-        long long q0;
+        int grp, lvl, q0;
         decode(it, grp, q0, lvl);
-        const long long qid = q0 + lane;
-        if (qid < p.BN) {
+        const int qid = q0 + lane;
+        if (qid < BN) {
             const int jb = (warp == 0) ? 0 : (2 * warp + 1);       // 0,3,5,7
             const int je = (warp == 0) ? 2 : (2 * warp + 2);       // 2,4,6,8
             const float ax = meta[buf].ax[lane], ay = meta[buf].ay[lane];
             const int o = meta[buf].x0[lane] & 3;
             const float4* wq = reinterpret_cast<const float4*>(win0 + buf * (kQ * kWinStride) + lane * kWinStride) +
                                (meta[buf].y0[lane] & 3) * 4;
-            const long long b = qid / p.N;
-            const long long n = qid - b * p.N;
-            const long long chan0 = b * (SF_NUM_LEVELS * kSide * kSide) + lvl * (kSide * kSide);
+            const int b = static_cast<unsigned>(qid) / static_cast<unsigned>(p.N);
+            const int n = qid - b * p.N;
+            // one 64-bit base per lane; channel offsets (i*9 + j) * N stay 32-bit
+            const long long obase = (static_cast<long long>(b) * (SF_NUM_LEVELS * kSide * kSide) + lvl * (kSide * kSide)) * p.N + n;
+            float* outf = reinterpret_cast<float*>(p.out[grp]) + obase;
+            __half* outh = reinterpret_cast<__half*>(p.out[grp]) + obase;
+            const int nine_n = kSide * p.N;
             float hprev[kSide];
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
@@ -187,11 +193,11 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < kSide; ++i) {
                         const float v = fmaf(ay, hcur[i] - hprev[i], hprev[i]);
-                        const long long idx = (chan0 + i * kSide + j) * p.N + n;
+                        const int off = i * nine_n + j * p.N;
                         if (kHalfOut) {
-                            reinterpret_cast<__half*>(p.out[grp])[idx] = __float2half_rn(v);
+                            outh[off] = __float2half_rn(v);
                         } else {
-                            __stcs(reinterpret_cast<float*>(p.out[grp]) + idx, v);
+                            __stcs(outf + off, v);
                         }
                     }
                 }
@@ -211,7 +217,9 @@ constexpr int kLookupSmem = 2 * kQ * kWinStride * 4 + 2 * static_cast<int>(sizeo
 int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaStream_t s) {
     LookupParams p = p_in;
     p.tiles = (p.BN + kQ - 1) / kQ;
-    SF_REQUIRE(p.tiles > 0 && p.tiles < (1ll << 31), "corr_lookup: bad query count %lld", p.BN);
+    SF_REQUIRE(p.tiles > 0 && p.BN * (SF_NUM_LEVELS * kSide * kSide) < (1ll << 31) &&
+                   p.tiles * groups * SF_NUM_LEVELS < (1ll << 31),
+               "corr_lookup: %lld queries per group exceed the 32-bit index range of the kernel", p.BN);
     p.items = p.tiles * groups * SF_NUM_LEVELS;
     // 4 CTAs of 55 KB per SM, persistent over the work items
     const int grid = static_cast<int>(std::min<long long>(p.items, 4ll * num_sms));
