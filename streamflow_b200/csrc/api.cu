@@ -31,6 +31,14 @@ void prof_after(int kind, cudaStream_t s) {
     if (kind == g_prof_kind && g_prof_stop) cudaEventRecord(g_prof_stop, s);
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("STREAMCORR_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 LevelGeom make_level_geom(int64_t h, int64_t w) {
     LevelGeom g;
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {

@@ -100,10 +100,12 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();        // everything above overlapped the previous kernel; its results are visible from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -238,7 +240,7 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
     const int grid = static_cast<int>(std::min<long long>(total, num_sms));
     prof_before(SF_KERNEL_CORR_GEMM, s);
-    corr_gemm_kernel<<<grid, 192, kSmemBytes, s>>>(args);
+    SF_CUDA_CHECK(launch_kernel(corr_gemm_kernel, dim3(grid), dim3(192), kSmemBytes, s, args));
     prof_after(SF_KERNEL_CORR_GEMM, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

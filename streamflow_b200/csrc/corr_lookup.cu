@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
 
     const int first = blockIdx.x, step = gridDim.x;
     float cx = 0.f, cy = 0.f;
+    pdl_launch();
+    pdl_wait();
     // prologue: item 0 fully staged, coordinates of item 1 in flight
     if (warp == 0) {
         load_coords(first, cx, cy);
@@ -226,7 +228,7 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
     auto launch = [&](auto kernel) -> int {
         SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLookupSmem));
         prof_before(SF_KERNEL_LOOKUP, s);
-        kernel<<<grid, 128, kLookupSmem, s>>>(p);
+        SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(128), static_cast<size_t>(kLookupSmem), s, p));
         prof_after(SF_KERNEL_LOOKUP, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;

@@ -54,6 +54,8 @@ __global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, lo
 // dense per-batch blocks (NCHW-contiguous or channels-last): plain vectorised sweep of the storage
 __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long sb0, long long sb1, int B,
                                     long long per_batch, unsigned* out_bits) {
+    pdl_launch();
+    pdl_wait();
     const float* f = blockIdx.y == 0 ? f0 : f1;
     const long long sb = blockIdx.y == 0 ? sb0 : sb1;
     const long long n4 = per_batch >> 2;
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     const int y0 = byi * 8, x0 = bxi * 8, k0 = blockIdx.y * 64;
     const long long sk = p.sk[which], sy = p.sy[which], sx = p.sx[which];
     const float* src = p.src[which] + b * p.sb[which];
+    pdl_launch();
+    pdl_wait();
     if (tid == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[which])));
     __syncthreads();
     const float scale = s_scale;
@@ -201,8 +205,8 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
         (reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0) {
         const int fb = static_cast<int>(std::min<long long>((per_batch / 4 + 255) / 256, 592));
         prof_before(SF_KERNEL_CORR_PACK, s);
-        absmax2_flat_kernel<<<dim3(fb, 2), 256, 0, s>>>(f1, f2, s1[0], s2[0], static_cast<int>(B), per_batch,
-                                                        amax_bits);
+        SF_CUDA_CHECK(launch_kernel(absmax2_flat_kernel, dim3(fb, 2), dim3(256), 0, s, f1, f2, (long long)s1[0],
+                                    (long long)s2[0], static_cast<int>(B), per_batch, amax_bits));
         prof_after(SF_KERNEL_CORR_PACK, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;
@@ -219,7 +223,7 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
 int launch_corr_pack(const PackParams& p, int64_t B, cudaStream_t s) {
     dim3 grid(p.bx * p.by, (p.D + 63) / 64, static_cast<unsigned>(2 * B));
     prof_before(SF_KERNEL_CORR_PACK, s);
-    corr_pack_kernel<<<grid, 256, 0, s>>>(p);
+    SF_CUDA_CHECK(launch_kernel(corr_pack_kernel, grid, dim3(256), 0, s, p));
     prof_after(SF_KERNEL_CORR_PACK, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {                                       // ---- E producer
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
 // grid = (ceil(N / 1024), P * C): one float4 per thread, no index arithmetic, every load in flight at once.
 template <typename T>
 __global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
+    pdl_launch();
+    pdl_wait();
     const int row = blockIdx.y;                          // p * C + c
     const int pb = row / p.C;
     const long long base = static_cast<long long>(row) * p.N;
@@ -262,7 +266,7 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
     const int grid = static_cast<int>(std::min<long long>(work, num_sms));
     SF_CUDA_CHECK(cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     prof_before(SF_KERNEL_GMA_AGGREGATE, s);
-    gma_aggregate_kernel<<<grid, kThreads, kSmemBytes, s>>>(args);
+    SF_CUDA_CHECK(launch_kernel(gma_aggregate_kernel, dim3(grid), dim3(kThreads), kSmemBytes, s, args));
     prof_after(SF_KERNEL_GMA_AGGREGATE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
@@ -272,9 +276,11 @@ int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
     dim3 grid((p.N + 1023) / 1024, p.P * p.C);
     prof_before(SF_KERNEL_GMA_FINALIZE, s);
     switch (p.fmap_dtype) {
-        case SF_DT_F32: gma_finalize_kernel<float><<<grid, 256, 0, s>>>(p); break;
-        case SF_DT_F16: gma_finalize_kernel<__half><<<grid, 256, 0, s>>>(p); break;
-        case SF_DT_BF16: gma_finalize_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+        case SF_DT_F32: SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<float>, grid, dim3(256), 0, s, p)); break;
+        case SF_DT_F16: SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<__half>, grid, dim3(256), 0, s, p)); break;
+        case SF_DT_BF16:
+            SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, p));
+            break;
         default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
     }
     prof_after(SF_KERNEL_GMA_FINALIZE, s);

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
     const int pb = blockIdx.y;
     const T* X = reinterpret_cast<const T*>(p.x) + static_cast<long long>(pb) * C * p.N;
 
+    pdl_launch();
+    pdl_wait();
     if (p.rscale != nullptr && tid < kTok && n0 + tid < p.N) {
         const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
         p.rscale[r] = __ldg(p.gamma) / __ldg(p.rowsum + r);
@@ -236,7 +238,7 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     auto launch = [&](auto kernel) -> int {
         SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         prof_before(SF_KERNEL_GMA_PROJ, s);
-        kernel<<<grid, 256, smem, s>>>(p);
+        SF_CUDA_CHECK(launch_kernel(kernel, grid, dim3(256), static_cast<size_t>(smem), s, p));
         prof_after(SF_KERNEL_GMA_PROJ, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;

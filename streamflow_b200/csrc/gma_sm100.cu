@@ -87,10 +87,12 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     auto unit_coords = [&](long long u, int& pb, int& mt, int& nt0, int& nt1) {
         const int per_p = p.m_tiles * p.chunks;
@@ -294,7 +296,7 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const int grid = static_cast<int>(std::min<long long>(units, num_sms));
     prof_before(SF_KERNEL_GMA_STATS, s);
-    gma_stats_kernel<<<grid, st::kThreads, st::kSmemBytes, s>>>(args);
+    SF_CUDA_CHECK(launch_kernel(gma_stats_kernel, dim3(grid), dim3(st::kThreads), st::kSmemBytes, s, args));
     prof_after(SF_KERNEL_GMA_STATS, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;

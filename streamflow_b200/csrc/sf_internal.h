@@ -35,6 +35,31 @@ void prof_after(int kind, cudaStream_t s);
 
 // Per-query correlation images are stored as 4x4 tiles (64 B each, tile-row-major): the lookup's 10x10 window then
 // touches ~3.25 x 3.25 sixty-four-byte blocks instead of 10 rows x 1.6 blocks of a row-major image.
+// Programmatic dependent launch: every kernel is launched with the stream-serialisation attribute, releases its
+// dependents right away (pdl_launch) and waits for its predecessor's memory (pdl_wait) only after its own
+// prologue (barrier init, TMEM allocation, descriptor prefetch, index setup), so launch latency and prologues of
+// the ~60 kernels of a step overlap the tail of the previous kernel.  STREAMCORR_PDL=0 disables the attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 struct LevelGeom {
     int h[SF_NUM_LEVELS], w[SF_NUM_LEVELS];       // valid cells
     int th[SF_NUM_LEVELS], tw[SF_NUM_LEVELS];     // tiles: ceil(h_l / 4), ceil(w_l / 4)
