@@ -129,10 +129,12 @@ SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk,
                      int64_t d, float scale, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
                      void* stream);
 
-/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] fp32; gamma: DEVICE pointer to 1 float (no host sync);
- * out: [P, C, N] fp32 (requires C == d: the reference's `project` is None, core/gma.py:86-89).         */
-SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const float* w_v,
-                     const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d,
+/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] of dtype w_dtype (SF_DT_F32, or SF_DT_F16 = weights the
+ * caller converted once: the faster path, the projection rounds them to fp16 anyway); gamma: DEVICE pointer to
+ * 1 float (no host sync); out: [P, C, N] fp32 (requires C == d: the reference's `project` is None,
+ * core/gma.py:86-89).                                                                                    */
+SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,
+                     int w_dtype, const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -115,8 +115,8 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     return launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s);
 }
 
-int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const float* w_v,
-                     const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d, void* workspace,
+int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,
+                     int w_dtype, const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d, void* workspace,
                      int64_t workspace_bytes, void* stream) {
     DeviceInfo di;
     if (int rc = query_device(&di)) return rc;
@@ -128,13 +128,16 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     const int64_t Npad = ws.Npad;
 
     GmaProjParams pv{};
-    pv.x = fmap; pv.x_dtype = fmap_dtype; pv.w = w_v;
+    SF_REQUIRE(w_dtype == SF_DT_F32 || w_dtype == SF_DT_F16, "gma_aggregate: w_v must be fp32 or fp16");
+    pv.x = fmap; pv.x_dtype = fmap_dtype;
+    pv.w = (w_dtype == SF_DT_F32) ? static_cast<const float*>(w_v) : nullptr;
+    pv.w16 = (w_dtype == SF_DT_F16) ? static_cast<const __half*>(w_v) : nullptr;
     pv.P = (int)P; pv.C = (int)C; pv.N = (int)N; pv.O = 128;
     pv.scale = 1.0f;
     pv.out = reinterpret_cast<__half*>(wsb + ws.v_off);
     pv.out_batch_stride = d * Npad; pv.ld = (int)Npad; pv.token_major = 0; pv.split = 0; pv.is_b = 0;
     pv.rowsum = rowsum; pv.gamma = gamma; pv.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
-    if (int rc = launch_gma_proj(pv, s)) return rc;
+    if (int rc = (w_dtype == SF_DT_F16) ? launch_gma_proj_v(pv, s) : launch_gma_proj(pv, s)) return rc;
 
     CUtensorMap tm_e, tm_v;
     const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;

@@ -144,7 +144,8 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
 struct GmaProjParams {
     const void* x;        // [P, C, N]
     int x_dtype;
-    const float* w;       // [O, C] rows o0 .. o0+O-1 used
+    const float* w;       // [O, C] rows o0 .. o0+O-1 used (fp32 path)
+    const __half* w16;    // [O, C] fp16 weights (gma_proj_v_kernel)
     int P, C, N, O;
     float scale;          // multiplies the result (q gets d^-1/2)
     __half* out;          // token-major: [P, Nrows, ldo] (ldo >= O) or channel-major: [P, O, ldn]
@@ -160,6 +161,7 @@ struct GmaProjParams {
     float* rscale;
 };
 int launch_gma_proj(const GmaProjParams& p, cudaStream_t s);
+int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s);
 
 struct GmaStatsParams {
     int P, N, Npad, Kp;

@@ -54,15 +54,15 @@ class AttentionHandle:
         return e.reshape(P, mt * 128)[:, :N]
 
 
-def _weight_2d(module, attr, param, rows, cols):
-    """fp32 contiguous [rows, cols] view of a conv weight, cached until the parameter is modified in place or
-    replaced (keeps ~6 us of reshape/detach off every call)."""
+def _weight_2d(module, attr, param, rows, cols, dtype=torch.float32):
+    """contiguous [rows, cols] copy/view of a conv weight in `dtype`, cached until the parameter is modified in
+    place or replaced (keeps the reshape / conversion off every call)."""
     key = (param.data_ptr(), param._version, param.dtype, param.device)
     cached = getattr(module, attr, None)
     if cached is None or cached[0] != key:
         w = param.detach().reshape(rows, cols)
-        if w.dtype != torch.float32 or not w.is_contiguous():
-            w = w.float().contiguous()
+        if w.dtype != dtype or not w.is_contiguous():
+            w = w.to(dtype).contiguous()
         cached = (key, w)
         object.__setattr__(module, attr, cached)
     return cached[1]
@@ -141,14 +141,16 @@ class Aggregate(nn.Module):
             x = x.contiguous()
         P, C, h, w = x.shape
         dev = x.device
-        wv = _weight_2d(self, "_wv_cache", self.to_v.weight, self.dim_head, C)
+        # the projection runs on fp16 tensor-core operands: convert the weights once, not once per CTA per call
+        wv = _weight_2d(self, "_wv_cache", self.to_v.weight, self.dim_head, C, torch.float16)
         gamma = self.gamma
         if gamma.dtype != torch.float32:
             gamma = gamma.detach().float()
         with _on_device(dev):
             out = torch.empty((P, C, h, w), dtype=torch.float32, device=dev)
             rc = _lib.lib().sf_gma_aggregate(attn.E.data_ptr(), attn.rowsum.data_ptr(), x.data_ptr(),
-                                             _lib.torch_dtype_code(x.dtype), wv.data_ptr(), gamma.data_ptr(),
+                                             _lib.torch_dtype_code(x.dtype), wv.data_ptr(), _lib.DT_F16,
+                                             gamma.data_ptr(),
                                              out.data_ptr(), P, C, attn.N, self.dim_head, attn._ws_ptr,
                                              attn._ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "sf_gma_aggregate")
