@@ -31,10 +31,15 @@ constexpr int kStageRows = kRows + 3;                    // window may start at 
 constexpr int kWinStride = kStageRows * kRowFloats + 4;  // 212 floats: 8 consecutive queries -> distinct bank quads
 constexpr int kSide = 2 * SF_RADIUS + 1;                 // 9
 
-__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool pred) {
+// 16-byte async copy, zero-filled when !pred.  The L2 evict_last policy keeps the window tiles resident for the
+// next refinement iteration (flow moves by ~1 px, so ~80 % of the tiles are touched again) while the 300 MB
+// softmax stream of the aggregation passes through L2 as evict_first.
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool pred, unsigned long long policy) {
     const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
     const int bytes = pred ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(d), "l"(src), "r"(bytes),
+                 "l"(policy)
+                 : "memory");
 }
 
 struct Meta {
@@ -97,6 +102,8 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
         meta[buf].y0[lane] = static_cast<int>(yf);
     };
     // stage B2: all threads, thread = (query, tile column): issue the window's 16-byte chunks
+    unsigned long long policy;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
     auto issue_window = [&](int it, int buf) {
         if (it < items) {
             int grp, lvl, q0;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
                         const int R = tr * 4 + rr;
                         if (R >= kStageRows) continue;
                         if (R < oy || R >= oy + kRows) continue;   // outside the window (same 64 B block)
-                        cp_async16_zfill(dst + R * kRowFloats, ok ? tile + rr * 4 : tile, ok);
+                        cp_async16_zfill(dst + R * kRowFloats, ok ? tile + rr * 4 : tile, ok, policy);
                     }
                 }
             }

@@ -19,7 +19,15 @@ namespace sf {
 namespace {
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kEScale = 4096.f;     // E = 2^12 * exp(.): keeps small weights out of the fp16 subnormals
+// E = 2^12 * exp(.): the scale keeps small weights out of the fp16 subnormals (folded into the exponent)
+
+// 2^x with one MUFU.EX2 (rel. error 2^-22; exp2f() adds a range check and two rescaling multiplies per element,
+// which made the pass-2 epilogue issue-bound at 13 instructions per logit)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ unsigned enc_ordered(float f) {
     const unsigned b = __float_as_uint(f);
@@ -169,7 +177,8 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
             const bool row_ok = row < p.N;
             const long long ridx = static_cast<long long>(pb) * p.N + row;
             float run_max = -INFINITY, run_sum = 0.f, mrow = 0.f;
-            if (p.pass == 2 && row_ok) mrow = dec_ordered(p.rowmax_bits[ridx]) * kLog2e;
+            // E = 2^(s*log2e - (rowmax*log2e - 12)): the 2^12 scale rides in the exponent
+            if (p.pass == 2 && row_ok) mrow = dec_ordered(p.rowmax_bits[ridx]) * kLog2e - 12.0f;
             for (int nt = nt0; nt < nt1; ++nt, ++local) {
                 const int acc = local & 1;
                 mbar_wait(&tfull[acc], (local >> 1) & 1);
@@ -208,37 +217,39 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
                         __half2 h[32];
+                        float sum0 = 0.f, sum1 = 0.f;
                         if (full) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
-                                const float a0 = exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale;
-                                const float a1 = exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale;
-                                const float b0 = exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale;
-                                const float b1 = exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale;
+                                const float a0 = ex2_approx(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow));
+                                const float a1 = ex2_approx(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow));
+                                const float b0 = ex2_approx(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow));
+                                const float b1 = ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow));
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                sum0 += a0 + b0;
+                                sum1 += a1 + b1;
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 const float a0 = (col0 + j < p.N)
-                                    ? exp2f(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                                    ? ex2_approx(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) : 0.f;
                                 const float a1 = (col0 + j + 1 < p.N)
-                                    ? exp2f(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                                    ? ex2_approx(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) : 0.f;
                                 const float b0 = (col0 + 32 + j < p.N)
-                                    ? exp2f(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) * kEScale : 0.f;
+                                    ? ex2_approx(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) : 0.f;
                                 const float b1 = (col0 + 32 + j + 1 < p.N)
-                                    ? exp2f(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) * kEScale : 0.f;
+                                    ? ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) : 0.f;
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                sum0 += a0 + b0;
+                                sum1 += a1 + b1;
                             }
                         }
-                        // row sum of the ROUNDED numerators (fp32 adds): sum_j E / rowsum == 1 for what is stored
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float2 f = __half22float2(h[j]);
-                            run_sum += f.x + f.y;
-                        }
+                        // row sums use the un-rounded fp32 numerators (two independent chains); against the stored
+                        // fp16 values the normalisation is off by at most 2^-11 / sqrt(N_eff) per row
+                        run_sum += sum0 + sum1;
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row
                             int4 o;
