@@ -1,0 +1,50 @@
+"""Back-to-back timing of each hot-path op (no event gaps between launches): true kernel cost at Sintel size."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+import streamflow_b200 as sfb
+from streamflow_b200 import _lib
+
+dev = torch.device("cuda", 0)
+host = bench.make_inputs(0)
+t = {k: host[k].to(dev) for k in ("fm_nhwc", "inps", "mfs", "coords")}
+class _A: pass
+att = sfb.Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).to(dev)
+agg = sfb.Aggregate(args=_A(), dim=128, heads=1, dim_head=128).to(dev)
+with torch.no_grad():
+    att.to_qk.weight.copy_(host["w_qk"].view(256, 128, 1, 1)); agg.to_v.weight.copy_(host["w_v"].view(128, 128, 1, 1)); agg.gamma.fill_(0.8)
+fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)
+blocks = [sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4) for i in range(3)]
+group = sfb.CorrGroup(blocks)
+handle = att(t["inps"])
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def timeit(name, fn, n=24, cold=False):
+    for _ in range(3): fn(0)
+    torch.cuda.synchronize()
+    if cold:
+        tot = 0.0
+        for i in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(i); e1.record(); torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        print(f"{name:28s} {tot / n * 1e3:8.1f} us  (L2 flushed before each launch, single launch incl. ~launch latency)")
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n): fn(i)
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name:28s} {e0.elapsed_time(e1) / n * 1e3:8.1f} us  (back-to-back x{n})")
+
+coords = [[t["coords"][it, i] for i in range(3)] for it in range(12)]
+timeit("group lookup (3 pairs)", lambda i: group(coords[i % 12]))
+timeit("group lookup (3 pairs)", lambda i: group(coords[i % 12]), cold=True)
+timeit("single lookup (1 pair)", lambda i: blocks[0](coords[i % 12][0]))
+timeit("aggregate (3 maps)", lambda i: agg(handle, t["mfs"]))
+timeit("aggregate (3 maps)", lambda i: agg(handle, t["mfs"]), cold=True)
+timeit("corr build (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4))
+timeit("attention (3 maps)", lambda i: att(t["inps"]), n=8)
+for which, nm in ((_lib.KERNEL_LOOKUP, "lookup"),):
+    pass
