@@ -85,30 +85,34 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     SF_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, P * N * 4, s));
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.acc_off, 0, P * N * d * 4, s));
 
-    CUtensorMap tm_q, tm_k;
+    CUtensorMap tm_q, tm_k, tm_e;
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
     if (int rc = make_tmap3(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.q_off, kp, N, P, kp * 2, N * kp * 2, 64,
                             128, "Q"))
         return rc;
     if (int rc = make_tmap3(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.k_off, kp, N, P, kp * 2, N * kp * 2, 64,
-                            64, "K"))
+                            256, "K"))
+        return rc;
+    // E is tile-major [P][m_tiles][Npad/64][128][64]: a 2-D view of 128-byte rows per map
+    const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
+    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 32,
+                            "E(store)"))
         return rc;
 
     GmaStatsParams sp{};
     sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = ws.Kp;
     sp.m_tiles = (int)((N + 127) / 128);
-    sp.pair_tiles = (sp.m_tiles + 1) / 2;
-    sp.n_tiles = (int)(Npad / 64);
-    const int64_t base_units = P * sp.pair_tiles;
+    sp.n_tiles = (int)((N + 255) / 256);
+    const int64_t base_units = P * sp.m_tiles;
     int chunks = (int)((4ll * di.sms + base_units - 1) / base_units);
     sp.chunks = std::max(1, std::min(chunks, sp.n_tiles));
     sp.rowmax_bits = reinterpret_cast<unsigned*>(wsb + ws.rowmax_off);
     sp.rowsum = rowsum;
     sp.E = static_cast<__half*>(E);
     sp.pass = 1;
-    if (int rc = launch_gma_stats(sp, tm_q, tm_k, di.sms, s)) return rc;
+    if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
     sp.pass = 2;
-    return launch_gma_stats(sp, tm_q, tm_k, di.sms, s);
+    return launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s);
 }
 
 int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,

@@ -1,0 +1,325 @@
+// G3: GMA softmax attention (core/gma.py:53-65) and motion-feature aggregation (core/gma.py:91-104) on
+// tcgen05 tensor cores.
+//
+// Q and K do not change across refinement iterations, so the softmax numerator is computed ONCE per clip and
+// kept in HBM as fp16 (E = 2^12 * exp(s - rowmax), tile-major 16 KB blocks, 99 MB per Sintel map -- trivial against 180 GB),
+// exactly the matrix the reference's autocast path re-casts to fp16 every iteration (core/gma.py:95-97).
+// Every iteration is then one streaming GEMM  acc = E . V^T  bound by reading E from HBM:
+//
+//   gma_stats_kernel      S = Q K^T tiles (128 x 256, K = d or 3d for hi/lo-split operands) in TMEM;
+//                         pass 1 reduces the row max, pass 2 writes E with TMA stores and the row sums.
+//   gma_aggregate_kernel  (gma_aggregate_sm100.cu) the per-iteration streaming GEMM with the fused epilogue.
+#include <cuda_bf16.h>
+
+#include "sf_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace sf {
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+// E = 2^12 * exp(.): the scale keeps small weights out of the fp16 subnormals (folded into the exponent)
+
+// 2^x with one MUFU.EX2 (rel. error 2^-22; exp2f() adds a range check and two rescaling multiplies per element,
+// which made the pass-2 epilogue issue-bound at 13 instructions per logit)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ unsigned enc_ordered(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// =====================================================================================================
+// stats: S = Q K^T
+// =====================================================================================================
+namespace st {
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quadrant, 128 columns each
+constexpr int kEpiBuf = 32 * 128;                       // 32 rows x 64 fp16
+constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBuf;
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+}  // namespace st
+
+struct GmaStatsArgs {
+    CUtensorMap tm_q, tm_k, tm_e;
+    GmaStatsParams p;
+};
+
+__global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
+    using namespace st;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tfull = bars + 2 * kStages;
+    uint64_t* tempty = bars + 2 * kStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const GmaStatsParams& p = args.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pass 1 only needs an approximate row max (any m within a few units of the true max keeps exp() in range and
+    // cancels in E / rowsum): use the hi parts alone (first d columns); pass 2 uses the full hi/lo-split K
+    const int kblocks = (p.pass == 1 ? (p.Kp / 3 + BK - 1) / BK : (p.Kp + BK - 1) / BK);
+    const int per_chunk = (p.n_tiles + p.chunks - 1) / p.chunks;
+    const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
+    const long long u_begin = units * blockIdx.x / gridDim.x;
+    const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.tm_q);
+        tma_prefetch_desc(&args.tm_k);
+        tma_prefetch_desc(&args.tm_e);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+    pdl_launch();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    auto unit_coords = [&](long long u, int& pb, int& mt, int& nt0, int& nt1) {
+        const int per_p = p.m_tiles * p.chunks;
+        pb = static_cast<int>(u / per_p);
+        const int r = static_cast<int>(u - static_cast<long long>(pb) * per_p);
+        mt = r / p.chunks;
+        const int ck = r - mt * p.chunks;
+        nt0 = ck * per_chunk;
+        nt1 = min(p.n_tiles, nt0 + per_chunk);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = u_begin; u < u_end; ++u) {
+                int pb, mt, nt0, nt1;
+                unit_coords(u, pb, mt, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = stage_base + stage * kStageBytes;
+                        mbar_expect_tx(&full[stage], kStageBytes);
+                        tma_load_3d(&args.tm_q, &full[stage], sa, kb * BK, mt * BM, pb);
+                        tma_load_3d(&args.tm_k, &full[stage], sa + kABytes, kb * BK, nt * BN, pb);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
+            int stage = 0, local = 0;
+            uint32_t phase = 0;
+            for (long long u = u_begin; u < u_end; ++u) {
+                int pb, mt, nt0, nt1;
+                unit_coords(u, pb, mt, nt0, nt1);
+                for (int nt = nt0; nt < nt1; ++nt, ++local) {
+                    const int acc = local & 1;
+                    mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+                        const uint64_t da = make_kmajor_sw128_desc(sa);
+                        const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit(&empty[stage]);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    umma_commit(&tfull[acc]);
+                }
+            }
+        }
+    } else {
+        const int e = warp - 2, quad = warp & 3, half = e >> 2;     // half: which 128 of the 256 key columns
+        uint8_t* bufs = epi_base + e * 2 * kEpiBuf;
+        const int kbk = p.Npad / 64;                                // 64-key blocks per row of E
+        int local = 0, buf_sel = 0;
+        for (long long u = u_begin; u < u_end; ++u) {
+            int pb, mt, nt0, nt1;
+            unit_coords(u, pb, mt, nt0, nt1);
+            const int row = mt * BM + quad * 32 + lane;
+            const bool row_ok = row < p.N;
+            const long long ridx = static_cast<long long>(pb) * p.N + row;
+            float run_max = -INFINITY, run_sum = 0.f, mrow = 0.f;
+            // E = 2^(s*log2e - (rowmax*log2e - 12)): the 2^12 scale rides in the exponent
+            if (p.pass == 2 && row_ok) mrow = dec_ordered(p.rowmax_bits[ridx]) * kLog2e - 12.0f;
+            for (int nt = nt0; nt < nt1; ++nt, ++local) {
+                const int acc = local & 1;
+                mbar_wait(&tfull[acc], (local >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cq = 0; cq < 2; ++cq) {            // this warp's two 64-key column groups
+                    const int cp = half * 2 + cq;
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr =
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cp * 64;
+                    tmem_ld_32x32(taddr, v0);
+                    tmem_ld_32x32(taddr + 32, v1);
+                    tmem_ld_wait();
+                    if (cq == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                    }
+                    const int col0 = nt * BN + cp * 64;
+                    if (col0 >= p.Npad) continue;
+                    const bool full = col0 + 64 <= p.N;     // warp-uniform: no per-element key masking needed
+                    if (p.pass == 1) {
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                run_max = fmaxf(run_max, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (col0 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v0[j]));
+                                if (col0 + 32 + j < p.N) run_max = fmaxf(run_max, __uint_as_float(v1[j]));
+                            }
+                        }
+                    } else {
+                        uint8_t* buf = bufs + buf_sel * kEpiBuf;
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                        __half2 h[32];
+                        float sum0 = 0.f, sum1 = 0.f;
+                        if (full) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float a0 = ex2_approx(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow));
+                                const float a1 = ex2_approx(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow));
+                                const float b0 = ex2_approx(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow));
+                                const float b1 = ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow));
+                                h[j >> 1] = __floats2half2_rn(a0, a1);
+                                h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                sum0 += a0 + b0;
+                                sum1 += a1 + b1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                const float a0 = (col0 + j < p.N)
+                                    ? ex2_approx(fmaf(__uint_as_float(v0[j]), kLog2e, -mrow)) : 0.f;
+                                const float a1 = (col0 + j + 1 < p.N)
+                                    ? ex2_approx(fmaf(__uint_as_float(v0[j + 1]), kLog2e, -mrow)) : 0.f;
+                                const float b0 = (col0 + 32 + j < p.N)
+                                    ? ex2_approx(fmaf(__uint_as_float(v1[j]), kLog2e, -mrow)) : 0.f;
+                                const float b1 = (col0 + 32 + j + 1 < p.N)
+                                    ? ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) : 0.f;
+                                h[j >> 1] = __floats2half2_rn(a0, a1);
+                                h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
+                                sum0 += a0 + b0;
+                                sum1 += a1 + b1;
+                            }
+                        }
+                        // row sums use the un-rounded fp32 numerators (two independent chains); against the stored
+                        // fp16 values the normalisation is off by at most 2^-11 / sqrt(N_eff) per row
+                        run_sum += sum0 + sum1;
+#pragma unroll
+                        for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row
+                            int4 o;
+                            o.x = *reinterpret_cast<int*>(&h[c16 * 4 + 0]);
+                            o.y = *reinterpret_cast<int*>(&h[c16 * 4 + 1]);
+                            o.z = *reinterpret_cast<int*>(&h[c16 * 4 + 2]);
+                            o.w = *reinterpret_cast<int*>(&h[c16 * 4 + 3]);
+                            *reinterpret_cast<int4*>(buf + lane * 128 + ((c16 ^ (lane & 7)) << 4)) = o;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            // E is tile-major: [P][m-tile][64-key block][128 rows][64 keys], 16 KB per tile
+                            tma_store_3d(&args.tm_e, buf, 0, (mt * kbk + (col0 >> 6)) * BM + quad * 32, pb);
+                            tma_store_commit();
+                        }
+                        buf_sel ^= 1;
+                    }
+                }
+            }
+            if (row_ok) {
+                if (p.pass == 1)
+                    atomicMax(p.rowmax_bits + ridx, enc_ordered(run_max));
+                else
+                    atomicAdd(p.rowsum + ridx, run_sum);
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+__global__ void fill_u32_kernel(unsigned* p, unsigned v, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace
+
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
+                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s) {
+    GmaStatsArgs args;
+    args.tm_q = tm_q;
+    args.tm_k = tm_k;
+    args.tm_e = tm_e;
+    args.p = p;
+    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kSmemBytes));
+    const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
+    const int grid = static_cast<int>(std::min<long long>(units, num_sms));
+    prof_before(SF_KERNEL_GMA_STATS, s);
+    SF_CUDA_CHECK(launch_kernel(gma_stats_kernel, dim3(grid), dim3(st::kThreads), st::kSmemBytes, s, args));
+    prof_after(SF_KERNEL_GMA_STATS, s);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s) {
+    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 1184));
+    prof_before(0, s);
+    fill_u32_kernel<<<blocks, 256, 0, s>>>(ptr, value, n);
+    prof_after(0, s);
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
+}  // namespace sf

@@ -165,16 +165,15 @@ int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s);
 
 struct GmaStatsParams {
     int P, N, Npad, Kp;
-    int m_tiles, pair_tiles;    // ceil(N/128), ceil(m_tiles/2): a CTA keeps two query tiles of Q resident
-    int n_tiles;                // 64-key tiles: Npad / 64
-    int chunks;                 // key-chunks per tile pair (work split)
+    int m_tiles, n_tiles;       // ceil(N/128), ceil(N/256)
+    int chunks;                 // key-chunks per m-tile (work split)
     unsigned* rowmax_bits;      // [P, N] ordered-int encoded running max (pass 1 out / pass 2 in)
     float* rowsum;              // [P, N] sum of stored E (pass 2 out, atomics)
-    __half* E;                  // tile-major [P][m_tiles][Npad/64][128][64]
+    __half* E;                  // [P, N, Npad]
     int pass;
 };
-int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k, int num_sms,
-                     cudaStream_t s);
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
+                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s);
 
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
@@ -189,5 +188,6 @@ struct GmaAggParams {
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
                          cudaStream_t s);
 int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s);
+int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
 
 }  // namespace sf
