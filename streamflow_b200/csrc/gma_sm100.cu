@@ -227,8 +227,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                                 const float b1 = ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow));
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
-                                sum0 += a0 + b0;
-                                sum1 += a1 + b1;
                             }
                         } else {
 #pragma unroll
@@ -243,12 +241,16 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                                     ? ex2_approx(fmaf(__uint_as_float(v1[j + 1]), kLog2e, -mrow)) : 0.f;
                                 h[j >> 1] = __floats2half2_rn(a0, a1);
                                 h[16 + (j >> 1)] = __floats2half2_rn(b0, b1);
-                                sum0 += a0 + b0;
-                                sum1 += a1 + b1;
                             }
                         }
-                        // row sums use the un-rounded fp32 numerators (two independent chains); against the stored
-                        // fp16 values the normalisation is off by at most 2^-11 / sqrt(N_eff) per row
+                        // row sum of the ROUNDED numerators (fp32 adds, two chains): sum_j E / rowsum == 1 for what is
+                        // stored (summing the un-rounded values leaves up to 2^-11 of normalisation error on peaked rows)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 f = __half22float2(h[j]);
+                            sum0 += f.x;
+                            sum1 += f.y;
+                        }
                         run_sum += sum0 + sum1;
 #pragma unroll
                         for (int c16 = 0; c16 < 8; ++c16) {   // 8 x 16-byte chunks (8 halfs) per 128 B row
