@@ -1,4 +1,7 @@
-"""Multi-threaded CPU port of the hot path on torch CPU ops (TEST / BASELINE INFRASTRUCTURE ONLY).
+"""Torch restatement of the hot path in the reference's own op sequence (TEST / BASELINE INFRASTRUCTURE ONLY).
+
+Runs on CPU (the timed baseline) and, being plain torch ops, on a CUDA device too -- the GPU tests use it as the
+"reference L1 on the same device" arm of the end-to-end flow comparison (tests/test_model_e2e_gpu.py).
 
 The reference's own implementation of this path is a sequence of PyTorch ops
 (``matmul``, ``avg_pool2d``, ``grid_sample``, 1x1 ``conv2d``, ``softmax``); the
@@ -40,7 +43,7 @@ class CpuCorrPyramid:
             lvl = F.avg_pool2d(lvl, 2, stride=2)
             self.levels.append(lvl)
         self.radius = radius
-        off = torch.arange(-radius, radius + 1, dtype=torch.float32)
+        off = torch.arange(-radius, radius + 1, dtype=torch.float32, device=fmap1.device)
         # window index i (slow) offsets x, j (fast) offsets y -- see SURVEY Appendix A.2
         self._dx = off.view(1, -1, 1).expand(1, off.numel(), off.numel())
         self._dy = off.view(1, 1, -1).expand(1, off.numel(), off.numel())
@@ -65,7 +68,7 @@ class CpuCorrPyramid:
 def cpu_attention(fmap: torch.Tensor, w_qk: torch.Tensor, heads: int = 1, dim_head: int = 128) -> torch.Tensor:
     """softmax(scale * q k^T) over all positions (core/gma.py:53-65) -> [P, heads, N, N]."""
     p, c, h, w = fmap.shape
-    qk = F.conv2d(fmap, w_qk.reshape(w_qk.shape[0], c, 1, 1))
+    qk = F.conv2d(fmap, w_qk.reshape(w_qk.shape[0], c, 1, 1).to(fmap.dtype))
     q, k = qk.chunk(2, dim=1)
     q = q.reshape(p, heads, dim_head, h * w) * dim_head ** -0.5
     k = k.reshape(p, heads, dim_head, h * w)
@@ -77,7 +80,7 @@ def cpu_aggregate(attn: torch.Tensor, fmap: torch.Tensor, w_v: torch.Tensor, gam
                   w_proj: torch.Tensor | None = None, heads: int = 1) -> torch.Tensor:
     """fmap + gamma * (attn . to_v(fmap)) (core/gma.py:91-104)."""
     p, c, h, w = fmap.shape
-    v = F.conv2d(fmap, w_v.reshape(w_v.shape[0], c, 1, 1))
+    v = F.conv2d(fmap, w_v.reshape(w_v.shape[0], c, 1, 1).to(fmap.dtype))
     inner = v.shape[1]
     v = v.reshape(p, heads, inner // heads, h * w)
     out = torch.matmul(attn, v.transpose(2, 3))            # [P, heads, N, dh]

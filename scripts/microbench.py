@@ -39,12 +39,29 @@ def timeit(name, fn, n=24, cold=False):
         print(f"{name:28s} {e0.elapsed_time(e1) / n * 1e3:8.1f} us  (back-to-back x{n})")
 
 coords = [[t["coords"][it, i] for i in range(3)] for it in range(12)]
-timeit("group lookup (3 pairs)", lambda i: group(coords[i % 12]))
-timeit("group lookup (3 pairs)", lambda i: group(coords[i % 12]), cold=True)
-timeit("single lookup (1 pair)", lambda i: blocks[0](coords[i % 12][0]))
-timeit("aggregate (3 maps)", lambda i: agg(handle, t["mfs"]))
-timeit("aggregate (3 maps)", lambda i: agg(handle, t["mfs"]), cold=True)
-timeit("corr build (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4))
-timeit("attention (3 maps)", lambda i: att(t["inps"]), n=8)
-for which, nm in ((_lib.KERNEL_LOOKUP, "lookup"),):
-    pass
+
+
+def graph_time(name, fn, n=12):
+    """GPU-only cost per call: n calls captured in one CUDA graph (no CPU launch cost), replayed 5x."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for i in range(2): fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            keep = [fn(i) for i in range(n)]
+    torch.cuda.synchronize()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:32s} {e0.elapsed_time(e1) / (5 * n) * 1e3:8.1f} us per call (graph of {n})")
+
+
+graph_time("group lookup (3 pairs)", lambda i: group(coords[i % 12]))
+graph_time("single-pair lookup", lambda i: blocks[0](coords[i % 12][0]))
+graph_time("aggregate (proj+agg+finalize)", lambda i: agg(handle, t["mfs"]))
+graph_time("corr build (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4), n=6)
+graph_time("corr build f16x2 (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4, precision="f16x2"), n=6)
+graph_time("attention (3 maps)", lambda i: att(t["inps"]), n=3)
