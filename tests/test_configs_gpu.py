@@ -1,0 +1,94 @@
+"""Parity at the sizes of BASELINE.json configs[2] (KITTI 376x1248, batched clips) and configs[3] (Spring 1080x1920)
+against the reference's torch op sequence run on the same GPU (oracle/torch_port.py, fp32, TF32 off), plus the
+streaming-window driver of configs[4] on one rank.  Tolerance: 1e-3 norm-wise (north_star)."""
+import pytest
+import torch
+
+from oracle import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+class _A:
+    pass
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.cuda.empty_cache()
+
+
+def test_kitti_batched_clips():
+    """47x156 (N = 7332, w/4 = 39 tiles; pooled widths 78/39/19 are ragged), B = 2 clips in one CorrBlock."""
+    from streamflow_b200 import CorrBlock, CorrGroup, coords_grid
+    torch.manual_seed(0)
+    B, h, w, d = 2, 47, 156, 256
+    fm = torch.randn(B, 3, h, w, d, device="cuda").half().float().permute(0, 1, 4, 2, 3)
+    ours = [CorrBlock(fm[:, i], fm[:, i + 1]) for i in range(2)]
+    refs = [tp.CpuCorrPyramid(fm[:, i], fm[:, i + 1]) for i in range(2)]
+    for l in range(4):
+        assert rel(ours[0].corr_pyramid[l], refs[0].levels[l]) < 1e-3
+    coords = [coords_grid(B, h, w, device="cuda").contiguous() + 4.0 * torch.randn(B, 2, h, w, device="cuda")
+              for _ in range(2)]
+    for i in range(2):
+        assert rel(ours[i](coords[i]), refs[i](coords[i])) < 1e-3
+    # pair-batched launch returns the (B T) C H W tensor of streamflow.py:132, rows ordered b*(T-1) + t
+    grouped = CorrGroup(ours)(coords)
+    stacked = torch.stack([refs[i](coords[i]) for i in range(2)], dim=1).flatten(0, 1)
+    assert grouped.shape == stacked.shape == (B * 2, 324, h, w)
+    assert rel(grouped, stacked) < 1e-3
+    half = CorrGroup(ours, out_dtype=torch.float16)(coords)
+    assert half.dtype == torch.float16 and rel(half.float(), stacked) < 2e-3
+
+
+def test_spring_size_pair():
+    """135x240 -> N = 32400: 4.2 GB level 0 per pair, 5.6 GB pyramid; GMA numerators 2.1 GB per map."""
+    from streamflow_b200 import Aggregate, Attention, CorrBlock, coords_grid
+    torch.manual_seed(1)
+    h, w, d = 135, 240, 256
+    fm = torch.randn(1, 2, h, w, d, device="cuda").half().float().permute(0, 1, 4, 2, 3)
+    blk = CorrBlock(fm[:, 0], fm[:, 1])
+    ref = tp.CpuCorrPyramid(fm[:, 0], fm[:, 1])
+    c = coords_grid(1, h, w, device="cuda").contiguous() + 6.0 * torch.randn(1, 2, h, w, device="cuda")
+    out, want = blk(c), ref(c)
+    assert out.shape == (1, 324, h, w)
+    assert rel(out, want) < 1e-3
+    # far out-of-bounds queries give exact zeros
+    far = c + 4000.0
+    assert float(blk(far).abs().max()) == 0.0
+    del blk, ref, out, want
+    torch.cuda.empty_cache()
+
+    att = Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    agg = Aggregate(args=_A(), dim=128, heads=1, dim_head=128).cuda()
+    with torch.no_grad():
+        att.to_qk.weight.normal_(0, 0.15)
+        agg.to_v.weight.normal_(0, 0.09)
+        agg.gamma.fill_(1.1)
+    inp = torch.relu(torch.randn(1, 128, h, w, device="cuda"))
+    mf = torch.randn(1, 128, h, w, device="cuda")
+    hd = att(inp)
+    got = agg(hd, mf)
+    attn = tp.cpu_attention(inp, att.to_qk.weight.detach().view(256, 128))
+    want = tp.cpu_aggregate(attn, mf, agg.to_v.weight.detach().view(128, 128), 1.1)
+    assert rel(got - mf, want - mf) < 1e-3
+
+
+def test_streaming_windows_single_rank():
+    """configs[4] driver on one rank: 10 frames -> 3 windows -> 9 flows in temporal order (demo.py:515-532)."""
+    from streamflow_b200 import dist as sfd
+    frames = [torch.full((3, 16, 24), float(i), device="cuda") for i in range(10)]
+
+    def fake_model(win):      # flow k of a window encodes its first frame index
+        return [torch.zeros(2, 16, 24, device="cuda") + float(win[k][0, 0, 0]) for k in range(3)]
+
+    flows = sfd.run_windows(frames, fake_model, T=4)
+    assert flows.shape == (9, 2, 16, 24)
+    assert [int(f[0, 0, 0]) for f in flows] == list(range(9))
