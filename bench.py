@@ -13,8 +13,11 @@ with no data-path collective (weak scaling); the only collective is the timing r
 
 JSON line (rank 0): value = flow fields per second over all ranks with inputs resident in HBM; e2e = the same
 through the public Python/C-ABI call path with pinned HOST buffers (H2D of every input and D2H of the results
-inside the timed region); roofline = dominant kernel (GMA aggregate, HBM-bound E stream) measured with CUDA
-events around the kernel launches inside the timed region; kernels = the same for lookup / corr GEMM;
+inside the timed region); roofline = dominant kernel (GMA aggregate, HBM-bound E stream); kernels = the same for
+lookup / corr GEMM.  Kernel durations are measured twice with CUDA events: `us_per_launch` = the kernel launched
+back-to-back inside one CUDA graph (12 launches with the step's own inputs; an event pair between two kernels costs
+~4 us of launch serialisation, 20 % of a 20 us kernel), `us_per_launch_event_pairs_in_step` = one event pair around
+every launch inside the eager step (upper bound);
 cpu_baseline = the torch-CPU port of the reference path on this host's cores.
 """
 from __future__ import annotations
@@ -281,29 +284,74 @@ def run_ours(args):
         torch.cuda.synchronize()
         return [a.elapsed_time(b) * 1e3 for a, b in pairs]       # microseconds
 
+    def graph_kernel_time(fn, calls, gma_mask=7, corr_mask=3, replays=5):
+        """Kernel duration without event gaps: `calls` back-to-back launches captured in ONE CUDA graph with the
+        library restricted to the kernel under test, CUDA events around `replays` replays."""
+        L.sf_debug_select_kernels(gma_mask, corr_mask)
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for i in range(2):
+                    fn(i)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    keep = [fn(i) for i in range(calls)]
+            torch.cuda.synchronize()
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(replays):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            del keep, g
+            return e0.elapsed_time(e1) * 1e3 / (replays * calls)
+        finally:
+            L.sf_debug_select_kernels(7, 3)
+
     kernels = {}
     if rank == 0:
         hbm = peaks["hbm_gbs"]
+        fm_views = resident["fm_nhwc"].permute(0, 1, 4, 2, 3)
+        g_blocks = [sfb.CorrBlock(fm_views[:, i], fm_views[:, i + 1], radius=4) for i in range(PAIRS)]
+        g_group = sfb.CorrGroup(g_blocks)
+        g_handle = att(resident["inps"])
+        us_graph = {
+            "gma_aggregate": graph_kernel_time(lambda i: agg(g_handle, resident["mfs"]), ITERS, gma_mask=2),
+            "corr_lookup": graph_kernel_time(
+                lambda i: g_group([resident["coords"][i % ITERS, j] for j in range(PAIRS)]), ITERS),
+            "corr_gemm": graph_kernel_time(
+                lambda i: sfb.CorrBlock(fm_views[:, i % PAIRS], fm_views[:, i % PAIRS + 1], radius=4), 6, corr_mask=2),
+        }
+        del g_blocks, g_group, g_handle
         us, n = kernel_time(_lib.KERNEL_GMA_AGGREGATE)
         npad = L.sf_gma_npad(N)
         bytes_agg = PAIRS * N * npad * 2 + PAIRS * CDIM * npad * 2           # E stream + V, per launch
-        kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / us / 1e3, "peak": hbm, "unit": "GB/s",
-                                    "frac": bytes_agg / us / 1e3 / hbm, "us_per_launch": us, "launches_timed": n,
+        ug = us_graph["gma_aggregate"]
+        kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / ug / 1e3, "peak": hbm, "unit": "GB/s",
+                                    "frac": bytes_agg / ug / 1e3 / hbm, "us_per_launch": ug,
+                                    "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
                                     "algorithmic_bytes": bytes_agg, "traffic": None,
                                     "flops": 2.0 * PAIRS * N * N * CDIM}
         us, n = kernel_time(_lib.KERNEL_LOOKUP)
         bytes_lk = 2904 * PAIRS * N
-        kernels["corr_lookup"] = {"bound": "hbm", "achieved": bytes_lk / us / 1e3, "peak": hbm, "unit": "GB/s",
-                                  "frac": bytes_lk / us / 1e3 / hbm, "us_per_launch": us, "launches_timed": n,
+        ug = us_graph["corr_lookup"]
+        kernels["corr_lookup"] = {"bound": "hbm", "achieved": bytes_lk / ug / 1e3, "peak": hbm, "unit": "GB/s",
+                                  "frac": bytes_lk / ug / 1e3 / hbm, "us_per_launch": ug,
+                                  "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
                                   "algorithmic_bytes": bytes_lk, "traffic": None,
                                   "note": "3 pairs per launch, coords random-walk; pyramid 783 MB >> L2"}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D
+        us_ev, us = us, us_graph["corr_gemm"]
         tf = flops / us / 1e6
         peak_tf = peaks["bf16_tflops"]
         out_bytes = 4 * N * sum((H8 >> l) * (((W8 >> l) + 3) // 4 * 4) for l in range(4))
         kernels["corr_gemm"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
-                                "frac": tf / peak_tf, "us_per_launch": us, "launches_timed": n,
+                                "frac": tf / peak_tf, "us_per_launch": us,
+                                "us_per_launch_event_pairs_in_step": us_ev, "launches_timed": n,
                                 "algorithmic_flops": flops, "store_gbs": out_bytes / us / 1e3,
                                 "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": None,
                                 "note": "fp16 operands (kind::f16), fp32 accumulate; output-store bound"}

@@ -77,6 +77,10 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_CORR_SIMT 8
 SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
+/* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = v projection,
+ * bit 1 = streaming GEMM, bit 2 = finalize) and sf_corr_build to (bit 0 = absmax + pack, bit 1 = GEMM), so bench.py
+ * can time one kernel back-to-back inside a CUDA graph.  Results are meaningless unless all bits are set (default). */
+SF_API void sf_debug_select_kernels(int gma_aggregate_mask, int corr_build_mask);
 
 /* ---- correlation pyramid -------------------------------------------------------------------------
  * Level l of the pyramid is a dense matrix [B*N, tiles_y * tiles_x * 16] fp32 (N = h*w): row b*N + y*w + x is the

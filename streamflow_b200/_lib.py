@@ -24,7 +24,8 @@ KERNEL_LOOKUP, KERNEL_CORR_GEMM, KERNEL_GMA_AGGREGATE, KERNEL_GMA_STATS = 1, 2, 
 KERNEL_CORR_PACK, KERNEL_GMA_PROJ, KERNEL_GMA_FINALIZE, KERNEL_CORR_SIMT = 5, 6, 7, 8
 
 EXPORTS = [
-    "sf_version", "sf_last_error", "sf_device_ok", "sf_launch_count", "sf_profile_kernel", "sf_corr_level_dims", "sf_corr_workspace_bytes",
+    "sf_version", "sf_last_error", "sf_device_ok", "sf_launch_count", "sf_profile_kernel",
+    "sf_debug_select_kernels", "sf_corr_level_dims", "sf_corr_workspace_bytes",
     "sf_corr_build", "sf_corr_lookup", "sf_corr_lookup_group", "sf_gma_npad", "sf_gma_e_elems",
     "sf_gma_workspace_bytes",
     "sf_gma_attention", "sf_gma_aggregate",
@@ -53,6 +54,8 @@ def lib() -> ctypes.CDLL:
     L.sf_launch_count.restype = c_int64
     L.sf_profile_kernel.argtypes = [c_int, c_void_p, c_void_p]
     L.sf_profile_kernel.restype = None
+    L.sf_debug_select_kernels.argtypes = [c_int, c_int]
+    L.sf_debug_select_kernels.restype = None
     L.sf_corr_level_dims.argtypes = [c_int64, c_int64, c_int, i64p, i64p, i64p, i64p]
     L.sf_corr_level_dims.restype = None
     L.sf_corr_workspace_bytes.argtypes = [c_int64, c_int64, c_int64, c_int64, c_int]

@@ -23,6 +23,10 @@ static thread_local int64_t g_launches = 0;
 static thread_local int g_prof_kind = 0;
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
 
+static thread_local int g_gma_mask = 7, g_corr_mask = 3;
+int debug_gma_mask() { return g_gma_mask; }
+int debug_corr_mask() { return g_corr_mask; }
+
 void prof_before(int kind, cudaStream_t s) {
     ++g_launches;
     if (kind == g_prof_kind && g_prof_start) cudaEventRecord(g_prof_start, s);
@@ -197,6 +201,11 @@ void sf_profile_kernel(int which, void* start, void* stop) {
     g_prof_stop = static_cast<cudaEvent_t>(stop);
 }
 
+void sf_debug_select_kernels(int gma_aggregate_mask, int corr_build_mask) {
+    g_gma_mask = gma_aggregate_mask;
+    g_corr_mask = corr_build_mask;
+}
+
 int sf_device_ok(void) {
     DeviceInfo di;
     return query_device(&di);
@@ -249,7 +258,9 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     SF_REQUIRE(D % 8 == 0, "corr_build: tensor-core modes need D %% 8 == 0 (got %lld); use SF_PREC_FP32_SIMT",
                (long long)D);
     unsigned* amax = reinterpret_cast<unsigned*>(wsb + ws.amax_off);
-    if (int rc = launch_absmax2(fmap1, fmap2, B, D, h, w, f1_strides, f2_strides, amax, s)) return rc;
+    const int parts = debug_corr_mask();
+    if (parts & 1)
+        if (int rc = launch_absmax2(fmap1, fmap2, B, D, h, w, f1_strides, f2_strides, amax, s)) return rc;
 
     PackParams pp{};
     pp.src[0] = fmap1; pp.src[1] = fmap2;
@@ -265,8 +276,11 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     pp.bx = (int)((w + 7) / 8); pp.by = (int)((h + 7) / 8);
     pp.amax_bits = amax;
     // tile-grid cells of levels 2-3 can lie outside every 8x8 source block: clear those (small) operands first
-    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.b_off[2], 0, ws.total - ws.b_off[2], s));
-    if (int rc = launch_corr_pack(pp, B, s)) return rc;
+    if (parts & 1) {
+        SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.b_off[2], 0, ws.total - ws.b_off[2], s));
+        if (int rc = launch_corr_pack(pp, B, s)) return rc;
+    }
+    if (!(parts & 2)) return SF_OK;
 
     CorrGemmParams gp{};
     gp.B = (int)B; gp.N = (int)N; gp.Kp = ws.Kp;

@@ -137,7 +137,9 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     pv.out = reinterpret_cast<__half*>(wsb + ws.v_off);
     pv.out_batch_stride = d * Npad; pv.ld = (int)Npad; pv.token_major = 0; pv.split = 0; pv.is_b = 0;
     pv.rowsum = rowsum; pv.gamma = gamma; pv.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
-    if (int rc = (w_dtype == SF_DT_F16) ? launch_gma_proj_v(pv, s) : launch_gma_proj(pv, s)) return rc;
+    const int parts = debug_gma_mask();
+    if (parts & 1)
+        if (int rc = (w_dtype == SF_DT_F16) ? launch_gma_proj_v(pv, s) : launch_gma_proj(pv, s)) return rc;
 
     CUtensorMap tm_e, tm_v;
     const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
@@ -157,8 +159,9 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     ap.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
     ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
     ap.out = out;
-    if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
-    return launch_gma_finalize(ap, s);
+    if (parts & 2)
+        if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
+    return (parts & 4) ? launch_gma_finalize(ap, s) : SF_OK;
 }
 
 }  // extern "C"

@@ -30,6 +30,8 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 // launch accounting + optional event bracketing of one kernel kind (see sf_profile_kernel)
+int debug_gma_mask();
+int debug_corr_mask();
 void prof_before(int kind, cudaStream_t s);
 void prof_after(int kind, cudaStream_t s);
 
