@@ -37,6 +37,9 @@ sys.path.insert(0, ROOT)
 H8, W8, D, T, ITERS, CDIM = 55, 128, 256, 4, 12, 128
 N = H8 * W8
 PAIRS = T - 1
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+# (profiles/r1c_ncu_full_summary.md); static because bench.py must not run under a profiler
+NCU_DRAM_BYTES = {"gma_aggregate": 321.4e6, "corr_lookup": 57.4e6, "corr_gemm": 222.6e6}
 METRIC = "flow frames/s (Sintel 436x1024, T=4, 12 iters); corr-lookup HBM GB/s"
 WORKLOAD = "sintel_436x1024_T4_12iters_hotpath"
 
@@ -401,7 +404,7 @@ def run_ours(args):
         kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / ug / 1e3, "peak": hbm, "unit": "GB/s",
                                     "frac": bytes_agg / ug / 1e3 / hbm, "us_per_launch": ug,
                                     "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
-                                    "algorithmic_bytes": bytes_agg, "traffic": None,
+                                    "algorithmic_bytes": bytes_agg, "traffic": NCU_DRAM_BYTES["gma_aggregate"],
                                     "flops": 2.0 * PAIRS * N * N * CDIM}
         us, n = kernel_time(_lib.KERNEL_LOOKUP)
         bytes_lk = 2904 * PAIRS * N
@@ -409,8 +412,9 @@ def run_ours(args):
         kernels["corr_lookup"] = {"bound": "hbm", "achieved": bytes_lk / ug / 1e3, "peak": hbm, "unit": "GB/s",
                                   "frac": bytes_lk / ug / 1e3 / hbm, "us_per_launch": ug,
                                   "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
-                                  "algorithmic_bytes": bytes_lk, "traffic": None,
-                                  "note": "3 pairs per launch, coords random-walk; pyramid 783 MB >> L2"}
+                                  "algorithmic_bytes": bytes_lk, "traffic": NCU_DRAM_BYTES["corr_lookup"],
+                                  "note": "3 pairs per launch, coords random-walk; pyramid 805 MB >> L2; the 27 MB "
+                                          "of stores mostly leave L2 after the kernel (cold ncu counts 2.4 MB)"}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D
         us_ev, us = us, us_graph["corr_gemm"]
@@ -421,7 +425,7 @@ def run_ours(args):
                                 "frac": tf / peak_tf, "us_per_launch": us,
                                 "us_per_launch_event_pairs_in_step": us_ev, "launches_timed": n,
                                 "algorithmic_flops": flops, "store_gbs": out_bytes / us / 1e3,
-                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": None,
+                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": NCU_DRAM_BYTES["corr_gemm"],
                                 "note": "fp16 operands (kind::f16), fp32 accumulate; output-store bound"}
 
         # the small helper kernels, for the step budget in DESIGN.md (event pair brackets the last launch of the

@@ -75,6 +75,7 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_GMA_PROJ 6
 #define SF_KERNEL_GMA_FINALIZE 7
 #define SF_KERNEL_CORR_SIMT 8
+#define SF_KERNEL_UPSAMPLE 9
 SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
 /* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = v projection,
@@ -140,6 +141,13 @@ SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk,
 SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,
                      int w_dtype, const float* gamma, float* out, int64_t P, int64_t C, int64_t N, int64_t d,
                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- convex flow upsampling -------------------------------------------------------
+ * Replaces SKFlow_MF8.upsample_flow (core/models/streamflow.py:82-93), ratio 8:
+ *   out[n, c, 8y+i, 8x+j] = sum_k softmax_k(mask[n, k*64 + i*8 + j, y, x]) * 8 * flow[n, c, y + k/3 - 1, x + k%3 - 1]
+ * flow: [N, 2, H, W] fp32 contiguous; mask: [N, 576, H, W] contiguous of dtype mask_dtype; out: [N, 2, 8H, 8W] fp32. */
+SF_API int sf_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
+                     int64_t W, int ratio, void* stream);
 
 #ifdef __cplusplus
 }

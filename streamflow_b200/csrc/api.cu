@@ -356,4 +356,15 @@ int sf_corr_lookup_group(int G, const float* const* levels, const float* const* 
     return lookup_common(G, levels, coords, out, out_dtype, B, h, w, radius, num_levels, stream);
 }
 
+int sf_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H, int64_t W,
+                     int ratio, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    SF_REQUIRE(flow && mask && out, "upsample_flow: null pointer argument");
+    SF_REQUIRE(ratio == 8, "upsample_flow: specialised for ratio 8 (got %d)", ratio);
+    SF_REQUIRE(N >= 1 && H >= 1 && W >= 1 && N < 65536 && H < 65536, "upsample_flow: bad shape");
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "upsample_flow: out must be 16-byte aligned");
+    return launch_upsample_flow(flow, mask, mask_dtype, out, N, H, W, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

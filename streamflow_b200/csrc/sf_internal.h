@@ -192,4 +192,7 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const C
 int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s);
 int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
 
+int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
+                         int64_t W, cudaStream_t s);
+
 }  // namespace sf

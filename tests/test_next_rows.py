@@ -1,0 +1,78 @@
+"""SURVEY 8(f) "next" rows: convex upsampling kernel (GPU), .flo wire format and InputPadder (CPU)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from streamflow_b200 import flowio
+from tests.helpers import rs_normal
+
+
+def ref_upsample(flow, mask, ratio=8):
+    """core/models/streamflow.py:82-93 restated."""
+    n, _, h, w = flow.shape
+    mask = torch.softmax(mask.view(n, 1, 9, ratio, ratio, h, w).float(), dim=2)
+    up = F.unfold(ratio * flow, [3, 3], padding=1).view(n, 2, 9, 1, 1, h, w)
+    up = torch.sum(mask * up, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(n, 2, ratio * h, ratio * w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((1, 55, 128), torch.float32), ((3, 55, 128), torch.float16),
+                                         ((2, 23, 37), torch.float32), ((1, 5, 3), torch.bfloat16)])
+def test_upsample_flow_matches_reference(shape, dtype):
+    from streamflow_b200 import upsample_flow
+    n, h, w = shape
+    flow = torch.from_numpy(rs_normal(80, (n, 2, h, w)) * 4).cuda()
+    mask = (torch.from_numpy(rs_normal(81, (n, 576, h, w))) * 2).cuda().to(dtype)
+    got = upsample_flow(flow, mask)
+    want = ref_upsample(flow, mask)
+    assert got.shape == (n, 2, 8 * h, 8 * w) and got.dtype == torch.float32
+    err = float((got - want).norm() / want.norm())
+    assert err < 1e-5, f"rel err {err:.3e}"
+
+
+@pytest.mark.gpu
+def test_patch_upsample_replaces_method():
+    from streamflow_b200 import patch_upsample
+
+    class Dummy:
+        def upsample_flow(self, flow, mask, ratio=8):
+            raise AssertionError("should have been patched")
+
+    patch_upsample(Dummy)
+    flow = torch.zeros(1, 2, 4, 4, device="cuda")
+    mask = torch.zeros(1, 576, 4, 4, device="cuda")
+    assert Dummy().upsample_flow(flow, mask).shape == (1, 2, 32, 32)
+
+
+def test_flo_roundtrip_and_layout(tmp_path):
+    flow = rs_normal(90, (2, 7, 11))
+    p = tmp_path / "a.flo"
+    flowio.write_flo(p, torch.from_numpy(flow))
+    raw = np.fromfile(p, np.uint8)
+    assert raw.size == 12 + 7 * 11 * 2 * 4
+    assert np.frombuffer(raw[:4].tobytes(), np.float32)[0] == np.float32(202021.25)
+    assert tuple(np.frombuffer(raw[4:12].tobytes(), np.int32)) == (11, 7)          # width, then height
+    body = np.frombuffer(raw[12:].tobytes(), np.float32).reshape(7, 11, 2)          # interleaved u, v
+    np.testing.assert_array_equal(body[..., 0], flow[0])
+    np.testing.assert_array_equal(body[..., 1], flow[1])
+    back = flowio.read_flo(p)
+    np.testing.assert_array_equal(back, np.transpose(flow, (1, 2, 0)))
+    (tmp_path / "bad.flo").write_bytes(b"\\x00" * 32)
+    with pytest.raises(ValueError):
+        flowio.read_flo(tmp_path / "bad.flo")
+
+
+def test_input_padder_sintel_and_kitti():
+    x = torch.arange(436 * 1024, dtype=torch.float32).view(1, 1, 436, 1024)
+    pad = flowio.InputPadder(x.shape)                       # sintel: 436 -> 440, two rows top and bottom
+    y, = pad.pad(x)
+    assert y.shape[-2:] == (440, 1024) and pad._pad == [0, 0, 2, 2]
+    assert torch.equal(y[..., 0, :], x[..., 0, :]) and torch.equal(y[..., -1, :], x[..., -1, :])   # replicate
+    assert torch.equal(pad.unpad(y), x)
+    k = torch.zeros(1, 3, 375, 1242)
+    padk = flowio.InputPadder(k.shape, mode="kitti")        # bottom-only vertical padding
+    assert padk._pad == [3, 3, 0, 1] and padk.pad(k)[0].shape[-2:] == (376, 1248)
+    assert padk.unpad(padk.pad(k)[0]).shape == k.shape
+    assert flowio.InputPadder((376, 1248))._pad == [0, 0, 0, 0]
