@@ -41,7 +41,7 @@ def test_state_dict_names_match_reference():
     assert list(att.state_dict()) == ["to_qk.weight"]
     assert sorted(agg.state_dict()) == ["gamma", "to_v.weight"]
     assert tuple(att.to_qk.weight.shape) == (256, 128, 1, 1) and tuple(agg.to_v.weight.shape) == (128, 128, 1, 1)
-    assert float(agg.gamma) == 0.0 and agg.project is None
+    assert float(agg.gamma.detach()) == 0.0 and agg.project is None
 
 
 def test_gma_small_vs_reference_golden():
