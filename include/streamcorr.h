@@ -130,9 +130,12 @@ SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d
 
 /* fmap: [P, C, N] (NCHW flattened, contiguous) of dtype fmap_dtype; w_qk: [2*d, C] fp32 contiguous
  * (rows [0,d) -> q, rows [d,2d) -> k, as nn.Conv2d(dim, 2*inner, 1).weight chunked, core/gma.py:56).   */
+/* precision: SF_PREC_F16 = q, k rounded to fp16 for the logit GEMM (the operand precision of the reference's own
+ * autocast path, core/models/streamflow.py:118-124); SF_PREC_F16X2 = hi/lo-split projections and logits
+ * (fp32-faithful, 3x the tensor-core work of this once-per-clip kernel).                                    */
 SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N,
-                     int64_t d, float scale, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
-                     void* stream);
+                     int64_t d, float scale, int precision, void* E, float* rowsum, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 
 /* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] of dtype w_dtype (SF_DT_F32, or SF_DT_F16 = weights the
  * caller converted once: the faster path, the projection rounds them to fp16 anyway); gamma: DEVICE pointer to

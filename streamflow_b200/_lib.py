@@ -75,7 +75,7 @@ def lib() -> ctypes.CDLL:
     L.sf_gma_e_elems.restype = c_int64
     L.sf_gma_workspace_bytes.argtypes = [c_int64, c_int64, c_int64, c_int64]
     L.sf_gma_workspace_bytes.restype = c_int64
-    L.sf_gma_attention.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float,
+    L.sf_gma_attention.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int,
                                    c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     L.sf_gma_attention.restype = c_int
     L.sf_gma_aggregate.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64,

@@ -12,7 +12,7 @@ struct GmaWs {
 
 GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     GmaWs ws{};
-    ws.Kp = static_cast<int>(3 * d);            // hi/lo split q, k: fp32-faithful logits (once per clip)
+    ws.Kp = static_cast<int>(3 * d);            // room for hi/lo-split q, k (SF_PREC_F16X2); SF_PREC_F16 uses d
     ws.Npad = align_up(N, 64);
     int64_t off = 0;
     ws.q_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
@@ -58,12 +58,17 @@ int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d) {
 }
 
 int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N, int64_t d,
-                     float scale, void* E, float* rowsum, void* workspace, int64_t workspace_bytes, void* stream) {
+                     float scale, int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
     DeviceInfo di;
     if (int rc = query_device(&di)) return rc;
     const GmaWs ws = gma_ws_layout(P, N, d);
     if (int rc = check_gma(P, C, N, d, workspace, workspace_bytes, ws)) return rc;
     SF_REQUIRE(fmap && w_qk && E && rowsum, "gma_attention: null pointer argument");
+    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2, "gma_attention: unknown precision mode %d",
+               precision);
+    const int split = (precision == SF_PREC_F16X2);
+    const int Kp = split ? ws.Kp : static_cast<int>(d);
     SF_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0, "gma_attention: E must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
@@ -74,7 +79,7 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     pq.P = (int)P; pq.C = (int)C; pq.N = (int)N; pq.O = 128;
     pq.scale = scale;
     pq.out = reinterpret_cast<__half*>(wsb + ws.q_off);
-    pq.out_batch_stride = N * ws.Kp; pq.ld = ws.Kp; pq.token_major = 1; pq.split = 1; pq.is_b = 0;
+    pq.out_batch_stride = N * Kp; pq.ld = Kp; pq.token_major = 1; pq.split = split; pq.is_b = 0;
     if (int rc = launch_gma_proj(pq, s)) return rc;
     GmaProjParams pk = pq;
     pk.w = w_qk + d * C; pk.scale = 1.0f;
@@ -86,7 +91,7 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.acc_off, 0, P * N * d * 4, s));
 
     CUtensorMap tm_q, tm_k, tm_e;
-    const uint64_t kp = static_cast<uint64_t>(ws.Kp);
+    const uint64_t kp = static_cast<uint64_t>(Kp);
     if (int rc = make_tmap3(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.q_off, kp, N, P, kp * 2, N * kp * 2, 64,
                             128, "Q"))
         return rc;
@@ -100,7 +105,7 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
         return rc;
 
     GmaStatsParams sp{};
-    sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = ws.Kp;
+    sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = Kp; sp.split = split;
     sp.m_tiles = (int)((N + 127) / 128);
     sp.n_tiles = (int)((N + 255) / 256);
     const int64_t base_units = P * sp.m_tiles;

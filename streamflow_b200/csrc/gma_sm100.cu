@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // pass 1 only needs an approximate row max (any m within a few units of the true max keeps exp() in range and
     // cancels in E / rowsum): use the hi parts alone (first d columns); pass 2 uses the full hi/lo-split K
-    const int kblocks = (p.pass == 1 ? (p.Kp / 3 + BK - 1) / BK : (p.Kp + BK - 1) / BK);
+    const int kblocks = ((p.pass == 1 && p.split) ? (p.Kp / 3 + BK - 1) / BK : (p.Kp + BK - 1) / BK);
     const int per_chunk = (p.n_tiles + p.chunks - 1) / p.chunks;
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const long long u_begin = units * blockIdx.x / gridDim.x;

@@ -16,6 +16,8 @@ The kernels are specialised for the shipped configuration heads=1, dim=dim_head=
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -75,9 +77,16 @@ def _check_cfg(dim, heads, dim_head):
             f"dim_head={dim_head}); no fallback path exists")
 
 
+_GMA_PRECISION = os.environ.get("STREAMCORR_GMA_PRECISION", "f16")
+
+
 class Attention(nn.Module):
+    """``precision`` (attribute, default from STREAMCORR_GMA_PRECISION, "f16"): "f16" rounds q, k to fp16 for the
+    logit GEMM -- the operand precision of the reference's autocast path; "f16x2" keeps them fp32-faithful."""
+
     def __init__(self, *, args, dim, max_pos_size=100, heads=4, dim_head=128):
         super().__init__()
+        self.precision = _GMA_PRECISION
         self.args = args
         self.heads = heads
         self.dim = dim
@@ -90,6 +99,8 @@ class Attention(nn.Module):
         _check_cfg(self.dim, self.heads, self.dim_head)
         if fmap.dim() != 4 or fmap.shape[1] != self.dim:
             raise StreamCorrError(f"Attention expects [P, {self.dim}, h, w], got {tuple(fmap.shape)}")
+        if self.precision not in ("f16", "f16x2"):
+            raise StreamCorrError(f"unknown GMA precision {self.precision!r}; choose 'f16' or 'f16x2'")
         if not fmap.is_cuda:
             raise StreamCorrError("Attention needs a CUDA tensor (no CPU fallback)")
         x = fmap.detach()
@@ -107,7 +118,8 @@ class Attention(nn.Module):
             ws_bytes = L.sf_gma_workspace_bytes(P, C, N, self.dim_head)
             ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
             rc = L.sf_gma_attention(x.data_ptr(), _lib.torch_dtype_code(x.dtype), wq.data_ptr(), P, C, N,
-                                    self.dim_head, float(self.scale), E.data_ptr(), rowsum.data_ptr(), ws_ptr,
+                                    self.dim_head, float(self.scale), _lib.PRECISIONS[self.precision], E.data_ptr(),
+                                    rowsum.data_ptr(), ws_ptr,
                                     ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "sf_gma_attention")
         return AttentionHandle(E, rowsum, ws_buf, ws_ptr, ws_bytes, (P, C, h, w))

@@ -23,9 +23,10 @@ def cuda(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-def make_modules(w_qk, w_v, gamma):
+def make_modules(w_qk, w_v, gamma, precision="f16"):
     from streamflow_b200 import Aggregate, Attention
     att = Attention(args=_Args(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    att.precision = precision
     agg = Aggregate(args=_Args(), dim=128, heads=1, dim_head=128).cuda()
     with torch.no_grad():
         att.to_qk.weight.copy_(cuda(w_qk).view(256, 128, 1, 1))
@@ -44,9 +45,10 @@ def test_state_dict_names_match_reference():
     assert float(agg.gamma.detach()) == 0.0 and agg.project is None
 
 
-def test_gma_small_vs_reference_golden():
+@pytest.mark.parametrize("precision", ["f16", "f16x2"])
+def test_gma_small_vs_reference_golden(precision):
     g = load_golden("gma_small.npz")
-    att, agg = make_modules(g["w_qk"], g["w_v"], g["gamma"])
+    att, agg = make_modules(g["w_qk"], g["w_v"], g["gamma"], precision)
     h = att(cuda(g["inp"]))
     attn = h.dense().cpu().numpy()
     assert attn.shape == g["attn"].shape
@@ -56,7 +58,8 @@ def test_gma_small_vs_reference_golden():
     out = agg(h, cuda(g["mf"])).cpu().numpy()
     e_out = rel_err(out, g["out"])
     e_delta = rel_err(out - g["mf"], g["out"] - g["mf"])
-    assert e_out < 1e-4 and e_delta < 1e-3, f"aggregate rel err {e_out:.3e}, on gamma*attn.v {e_delta:.3e}"
+    print(f"[{precision}] attention rel err {e_attn:.2e}, aggregate {e_out:.2e}, gamma*attn.v {e_delta:.2e}")
+    assert e_out < 2e-4 and e_delta < 1e-3, f"aggregate rel err {e_out:.3e}, on gamma*attn.v {e_delta:.3e}"
     # calling again (next refinement iteration) with new motion features reuses E and the zeroed accumulator
     mf2 = rs_normal(77, g["mf"].shape)
     out2 = agg(h, cuda(mf2)).cpu().numpy()
