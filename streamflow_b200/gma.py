@@ -77,12 +77,14 @@ def _check_cfg(dim, heads, dim_head):
             f"dim_head={dim_head}); no fallback path exists")
 
 
-_GMA_PRECISION = os.environ.get("STREAMCORR_GMA_PRECISION", "f16")
+_GMA_PRECISION = os.environ.get("STREAMCORR_GMA_PRECISION", "f16x2")
 
 
 class Attention(nn.Module):
-    """``precision`` (attribute, default from STREAMCORR_GMA_PRECISION, "f16"): "f16" rounds q, k to fp16 for the
-    logit GEMM -- the operand precision of the reference's autocast path; "f16x2" keeps them fp32-faithful."""
+    """``precision`` (attribute, default from STREAMCORR_GMA_PRECISION, "f16x2"): "f16x2" keeps the q/k projections
+    and logits fp32-faithful (hi/lo-split fp16 operands; measured 1.6e-4 on the attention matrix vs the fp32 oracle);
+    "f16" rounds q, k to fp16 for the logit GEMM -- the operand precision of the reference's own autocast path, 7e-4
+    vs the fp32 oracle, and 4 % faster on the whole step."""
 
     def __init__(self, *, args, dim, max_pos_size=100, heads=4, dim_head=128):
         super().__init__()

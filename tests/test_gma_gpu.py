@@ -23,7 +23,7 @@ def cuda(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-def make_modules(w_qk, w_v, gamma, precision="f16"):
+def make_modules(w_qk, w_v, gamma, precision="f16x2"):
     from streamflow_b200 import Aggregate, Attention
     att = Attention(args=_Args(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
     att.precision = precision
