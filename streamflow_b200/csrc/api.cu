@@ -295,6 +295,12 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     gp.amax_bits = amax;
     gp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
 
+    // resident-A kernel when the packed K fits in shared memory (STREAMCORR_GEMM=stream forces the streaming one)
+    static const bool force_stream = [] {
+        const char* e = getenv("STREAMCORR_GEMM");
+        return e && strcmp(e, "stream") == 0;
+    }();
+    const bool use_ra = corr_gemm_ra_supported(ws.Kp) && !force_stream;
     CUtensorMap tm_a, tm_b[SF_NUM_LEVELS], tm_out[SF_NUM_LEVELS];
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
     if (int rc = make_tmap3(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.a_off, kp, N, B, kp * 2, N * kp * 2, 64,
@@ -303,13 +309,14 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         const uint64_t rows = static_cast<uint64_t>(g.img[l]);
         if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
-                                rows * kp * 2, 64, 256, "B"))
+                                rows * kp * 2, 64, use_ra ? 128 : 256, "B"))
             return rc;
         if (int rc = make_tmap3(&tm_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, levels[l], rows, N, B, rows * 4,
                                 N * rows * 4, 32, 32, "level"))
             return rc;
     }
-    return launch_corr_gemm(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s);
+    return use_ra ? launch_corr_gemm_ra(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s)
+                  : launch_corr_gemm(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s);
 }
 
 static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,
