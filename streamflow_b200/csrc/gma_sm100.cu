@@ -290,12 +290,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     }
 }
 
-__global__ void fill_u32_kernel(unsigned* p, unsigned v, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        p[i] = v;
-}
-
 }  // namespace
 
 int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
@@ -311,15 +305,6 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     prof_before(SF_KERNEL_GMA_STATS, s);
     SF_CUDA_CHECK(launch_kernel(gma_stats_kernel, dim3(grid), dim3(st::kThreads), st::kSmemBytes, s, args));
     prof_after(SF_KERNEL_GMA_STATS, s);
-    SF_CUDA_CHECK(cudaGetLastError());
-    return SF_OK;
-}
-
-int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s) {
-    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 1184));
-    prof_before(0, s);
-    fill_u32_kernel<<<blocks, 256, 0, s>>>(ptr, value, n);
-    prof_after(0, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
