@@ -92,3 +92,86 @@ def test_streaming_windows_single_rank():
     flows = sfd.run_windows(frames, fake_model, T=4)
     assert flows.shape == (9, 2, 16, 24)
     assert [int(f[0, 0, 0]) for f in flows] == list(range(9))
+
+
+def test_kitti_gma_24_maps():
+    """configs[2] on one GPU: 8 clips x 3 pairs = 24 attention maps at 47x156 (2.6 GB of fp16 numerators)."""
+    from streamflow_b200 import Aggregate, Attention
+    torch.manual_seed(2)
+    P, h, w = 24, 47, 156
+    att = Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    agg = Aggregate(args=_A(), dim=128, heads=1, dim_head=128).cuda()
+    with torch.no_grad():
+        att.to_qk.weight.normal_(0, 0.15)
+        agg.to_v.weight.normal_(0, 0.09)
+        agg.gamma.fill_(0.9)
+    inp = torch.relu(torch.randn(P, 128, h, w, device="cuda"))
+    mf = torch.randn(P, 128, h, w, device="cuda")
+    hd = att(inp)
+    got = agg(hd, mf)
+    for p0 in (0, 11, 23):      # reference on single maps keeps the fp32 N x N matrix small
+        attn = tp.cpu_attention(inp[p0:p0 + 1], att.to_qk.weight.detach().view(256, 128))
+        want = tp.cpu_aggregate(attn, mf[p0:p0 + 1], agg.to_v.weight.detach().view(128, 128), 0.9)
+        assert rel(got[p0:p0 + 1] - mf[p0:p0 + 1], want - mf[p0:p0 + 1]) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_aggregate_low_precision_motion_features(dtype):
+    """Aggregate accepts fp16 / bf16 motion features (templated projection + finalize); result is fp32."""
+    from streamflow_b200 import Aggregate, Attention
+    torch.manual_seed(3)
+    P, h, w = 2, 24, 40
+    att = Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    agg = Aggregate(args=_A(), dim=128, heads=1, dim_head=128).cuda()
+    with torch.no_grad():
+        att.to_qk.weight.normal_(0, 0.15)
+        agg.to_v.weight.normal_(0, 0.09)
+        agg.gamma.fill_(1.3)
+    inp = torch.relu(torch.randn(P, 128, h, w, device="cuda"))
+    mf = torch.randn(P, 128, h, w, device="cuda").to(dtype)
+    got = agg(att(inp), mf)
+    assert got.dtype == torch.float32
+    attn = tp.cpu_attention(inp, att.to_qk.weight.detach().view(256, 128))
+    want = tp.cpu_aggregate(attn, mf.float(), agg.to_v.weight.detach().view(128, 128), 1.3)
+    assert rel(got - mf.float(), want - mf.float()) < 1e-3
+
+
+def test_whole_step_is_cuda_graph_capturable():
+    """Every entry point only enqueues work (no host sync, no allocation inside the library): a whole hot-path step
+    can be captured in a CUDA graph and replayed with new inputs in the same buffers."""
+    import streamflow_b200 as sfb
+    torch.manual_seed(4)
+    h, w = 24, 32
+    fm = torch.randn(1, 3, h, w, 64, device="cuda").half().float().permute(0, 1, 4, 2, 3)
+    inp = torch.relu(torch.randn(2, 128, h, w, device="cuda"))
+    mf = torch.randn(2, 128, h, w, device="cuda")
+    coords = [sfb.coords_grid(1, h, w, device="cuda").contiguous() + torch.randn(1, 2, h, w, device="cuda") for _ in range(2)]
+    att = sfb.Attention(args=_A(), dim=128, heads=1, max_pos_size=160, dim_head=128).cuda()
+    agg = sfb.Aggregate(args=_A(), dim=128, heads=1, dim_head=128).cuda()
+    with torch.no_grad():
+        att.to_qk.weight.normal_(0, 0.15)
+        agg.to_v.weight.normal_(0, 0.09)
+        agg.gamma.fill_(0.7)
+
+    def step():
+        blocks = [sfb.CorrBlock(fm[:, i], fm[:, i + 1]) for i in range(2)]
+        feats = sfb.CorrGroup(blocks)(coords)
+        return feats, agg(att(inp), mf)
+
+    eager = [t.clone() for t in step()]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            out = step()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], eager[0])
+    assert rel(out[1], eager[1]) < 1e-6          # the split-tile reduction order (atomics) may differ
+    mf.add_(1.0)                                 # new inputs in the same buffers
+    g.replay()
+    torch.cuda.synchronize()
+    want = step()[1]
+    assert rel(out[1], want) < 1e-6
