@@ -42,9 +42,14 @@ __device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, b
                  : "memory");
 }
 
+// Per-item metadata, written once by warp 0 (lane = query) so that neither the 128 loader threads nor the 128
+// interpolation threads repeat divisions or 64-bit address arithmetic.
 struct Meta {
     float ax[kQ], ay[kQ];
     int x0[kQ], y0[kQ];
+    const float* img[kQ];        // this query's correlation image at the item's level (nullptr: query out of range)
+    unsigned out_off[kQ];        // element offset of out[b, lvl*81, n] inside the group's output tensor
+    int grp, lvl;
 };
 
 // Persistent, software-pipelined: a CTA walks work items (32 queries x 1 level) with stride gridDim.x and keeps
@@ -62,61 +67,74 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     const int warp = tid >> 5;
     const int items = static_cast<int>(p.items), tiles = static_cast<int>(p.tiles), BN = static_cast<int>(p.BN);
 
-    // item -> (group, query tile, level); levels of one tile are adjacent items.  All index math is 32-bit
-    // (the launcher checks the ranges): 64-bit multiplies/divides were half of the instruction stream.
+    // item -> (group, query tile, level); levels of one tile are adjacent items.  Only warp 0 decodes (32-bit math).
     auto decode = [&](int it, int& grp, int& q0, int& lvl) {
         lvl = it & 3;
         const unsigned t = static_cast<unsigned>(it) >> 2;
         grp = static_cast<int>(t / static_cast<unsigned>(tiles));
         q0 = static_cast<int>(t - static_cast<unsigned>(grp) * tiles) * kQ;
     };
-    // stage A: warp 0 fetches the coordinates of an item into registers
-    auto load_coords = [&](int it, float& cx, float& cy) {
-        cx = cy = -1e30f;
+    // stage A: warp 0 fetches the coordinates of an item into registers (and remembers where its outputs go)
+    struct Pending {
+        float cx, cy;
+        int grp, lvl, qid, b, n;
+    };
+    auto load_coords = [&](int it, Pending& pd) {
+        pd.cx = pd.cy = -1e30f;
+        pd.qid = -1;
+        pd.grp = pd.lvl = pd.b = pd.n = 0;
         if (it < items) {
-            int grp, lvl, q0;
-            decode(it, grp, q0, lvl);
+            int q0;
+            decode(it, pd.grp, q0, pd.lvl);
             const int qid = q0 + lane;
             if (qid < BN) {
-                const int b = static_cast<unsigned>(qid) / static_cast<unsigned>(p.N);
-                const int n = qid - b * p.N;
-                const float* c = p.coords[grp] + static_cast<long long>(b) * 2 * p.N + n;
-                cx = __ldg(c);
-                cy = __ldg(c + p.N);
+                pd.qid = qid;
+                pd.b = (p.N >= BN) ? 0 : static_cast<int>(static_cast<unsigned>(qid) / static_cast<unsigned>(p.N));
+                pd.n = qid - pd.b * p.N;
+                const float* c = p.coords[pd.grp] + static_cast<long long>(pd.b) * 2 * p.N + pd.n;
+                pd.cx = __ldg(c);
+                pd.cy = __ldg(c + p.N);
             }
         }
     };
     // stage B1: warp 0 turns coordinates into the window origin + fractions of the item's level
-    auto write_meta = [&](int it, int buf, float cx, float cy) {
+    auto write_meta = [&](int it, int buf, const Pending& pd) {
         if (it >= items) return;
-        const int lvl = it & 3;
+        const int lvl = pd.lvl;
         const float inv = 1.0f / static_cast<float>(1 << lvl);
         // Far outside the image every tap is zero; clamping keeps the int conversion defined
         // (NaN / missing coordinates clamp to the lower bound and yield zeros).
-        const float X0 = fminf(fmaxf(cx * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.wl[lvl] + 8));
-        const float Y0 = fminf(fmaxf(cy * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.hl[lvl] + 8));
+        const float X0 = fminf(fmaxf(pd.cx * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.wl[lvl] + 8));
+        const float Y0 = fminf(fmaxf(pd.cy * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.hl[lvl] + 8));
         const float xf = floorf(X0), yf = floorf(Y0);
-        meta[buf].ax[lane] = X0 - xf;
-        meta[buf].ay[lane] = Y0 - yf;
-        meta[buf].x0[lane] = static_cast<int>(xf);
-        meta[buf].y0[lane] = static_cast<int>(yf);
+        Meta& m = meta[buf];
+        m.ax[lane] = X0 - xf;
+        m.ay[lane] = Y0 - yf;
+        m.x0[lane] = static_cast<int>(xf);
+        m.y0[lane] = static_cast<int>(yf);
+        m.img[lane] = pd.qid >= 0 ? p.lvl[pd.grp][lvl] + static_cast<long long>(pd.qid) * p.img[lvl] : nullptr;
+        m.out_off[lane] = static_cast<unsigned>((pd.b * (SF_NUM_LEVELS * kSide * kSide) + lvl * (kSide * kSide)) * p.N + pd.n);
+        if (lane == 0) {
+            m.grp = pd.grp;
+            m.lvl = lvl;
+        }
     };
-    // stage B2: all threads, thread = (query, tile column): issue the window's 16-byte chunks
     unsigned long long policy;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    // stage B2: all threads, thread = (query, tile column): issue the window's 16-byte chunks
     auto issue_window = [&](int it, int buf) {
         if (it < items) {
-            int grp, lvl, q0;
-            decode(it, grp, q0, lvl);
+            const Meta& m = meta[buf];
+            const int lvl = m.lvl;
             const int th = p.th[lvl], tw = p.tw[lvl];
             const int q = tid >> 2, j = tid & 3;
-            const int qid = q0 + q;
-            const int x0 = meta[buf].x0[q], y0 = meta[buf].y0[q];
+            const float* base = m.img[q];
+            const int x0 = m.x0[q], y0 = m.y0[q];
             const int ox = x0 & 3, oy = y0 & 3;             // window origin inside its first tile
             const int txc = (x0 >> 2) + j, ty0 = y0 >> 2;
-            if (qid < BN && 4 * j < ox + kRows) {           // tile column j overlaps window columns ox .. ox+9
+            if (base != nullptr && 4 * j < ox + kRows) {    // tile column j overlaps window columns ox .. ox+9
                 const bool colok = (txc >= 0) && (txc < tw);
-                const float* base = p.lvl[grp][lvl] + static_cast<long long>(qid) * p.img[lvl];
+                const unsigned rowmask = ((1u << kRows) - 1u) << oy;      // staged rows covered by the window
                 float* dst = win0 + buf * (kQ * kWinStride) + q * kWinStride + j * 4;
 #pragma unroll
                 for (int tr = 0; tr < 4; ++tr) {            // tile row: one 64-bit address per 64-byte tile
@@ -127,8 +145,8 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
                     for (int rr = 0; rr < 4; ++rr) {        // row inside the tile: constant offsets from here on
                         const int R = tr * 4 + rr;
                         if (R >= kStageRows) continue;
-                        if (R < oy || R >= oy + kRows) continue;   // outside the window (same 64 B block)
-                        cp_async16_zfill(dst + R * kRowFloats, ok ? tile + rr * 4 : tile, ok, policy);
+                        if (!(rowmask & (1u << R))) continue;      // outside the window (same 64 B block)
+                        cp_async16_zfill(dst + R * kRowFloats, tile + (ok ? rr * 4 : 0), ok, policy);
                     }
                 }
             }
@@ -137,14 +155,14 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     };
 
     const int first = blockIdx.x, step = gridDim.x;
-    float cx = 0.f, cy = 0.f;
+    Pending pd;
     pdl_launch();
     pdl_wait();
     // prologue: item 0 fully staged, coordinates of item 1 in flight
     if (warp == 0) {
-        load_coords(first, cx, cy);
-        write_meta(first, 0, cx, cy);
-        load_coords(first + step, cx, cy);
+        load_coords(first, pd);
+        write_meta(first, 0, pd);
+        load_coords(first + step, pd);
     }
     __syncthreads();
     issue_window(first, 0);
@@ -152,8 +170,8 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     int buf = 0;
     for (int it = first; it < items; it += step, buf ^= 1) {
         if (warp == 0) {
-            write_meta(it + step, buf ^ 1, cx, cy);
-            load_coords(it + 2 * step, cx, cy);
+            write_meta(it + step, buf ^ 1, pd);
+            load_coords(it + 2 * step, pd);
         }
         __syncthreads();                                    // meta[buf^1] visible; win[buf^1] free (read 2 items ago)
         issue_window(it + step, buf ^ 1);
@@ -161,23 +179,19 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
         __syncthreads();
 
         // stage C: lane = query; warp w owns y-offsets j in [jb, je]
-        int grp, lvl, q0;
-        decode(it, grp, q0, lvl);
-        const int qid = q0 + lane;
-        if (qid < BN) {
+        const Meta& m = meta[buf];
+        if (m.img[lane] != nullptr) {
             const int jb = (warp == 0) ? 0 : (2 * warp + 1);       // 0,3,5,7
             const int je = (warp == 0) ? 2 : (2 * warp + 2);       // 2,4,6,8
-            const float ax = meta[buf].ax[lane], ay = meta[buf].ay[lane];
-            const int o = meta[buf].x0[lane] & 3;
+            const float ax = m.ax[lane], ay = m.ay[lane];
+            const int o = m.x0[lane] & 3;
             const float4* wq = reinterpret_cast<const float4*>(win0 + buf * (kQ * kWinStride) + lane * kWinStride) +
-                               (meta[buf].y0[lane] & 3) * 4;
-            const int b = static_cast<unsigned>(qid) / static_cast<unsigned>(p.N);
-            const int n = qid - b * p.N;
-            // one 64-bit base per lane; channel offsets (i*9 + j) * N stay 32-bit
-            const long long obase = (static_cast<long long>(b) * (SF_NUM_LEVELS * kSide * kSide) + lvl * (kSide * kSide)) * p.N + n;
-            float* outf = reinterpret_cast<float*>(p.out[grp]) + obase;
-            __half* outh = reinterpret_cast<__half*>(p.out[grp]) + obase;
-            const int nine_n = kSide * p.N;
+                               (m.y0[lane] & 3) * 4;
+            // uniform 64-bit base (kernel parameter) + 32-bit per-lane element offset: one IMAD.WIDE per store
+            float* const outf = reinterpret_cast<float*>(p.out[m.grp]);
+            __half* const outh = reinterpret_cast<__half*>(p.out[m.grp]);
+            const unsigned ooff = m.out_off[lane];
+            const unsigned nine_n = static_cast<unsigned>(kSide * p.N), un = static_cast<unsigned>(p.N);
             float hprev[kSide];
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
@@ -198,16 +212,16 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kSide; ++i) hcur[i] = fmaf(ax, u[i + 1] - u[i], u[i]);
                 if (r > jb) {
-                    const int j = r - 1;
+                    unsigned off = ooff + static_cast<unsigned>(r - 1) * un;      // channel i*9 + j, j = r - 1
 #pragma unroll
                     for (int i = 0; i < kSide; ++i) {
                         const float v = fmaf(ay, hcur[i] - hprev[i], hprev[i]);
-                        const int off = i * nine_n + j * p.N;
                         if (kHalfOut) {
                             outh[off] = __float2half_rn(v);
                         } else {
                             __stcs(outf + off, v);
                         }
+                        off += nine_n;
                     }
                 }
 #pragma unroll
