@@ -73,13 +73,13 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_GMA_STATS 4
 #define SF_KERNEL_CORR_PACK 5
 #define SF_KERNEL_GMA_PROJ 6
-#define SF_KERNEL_GMA_FINALIZE 7
+#define SF_KERNEL_GMA_FINALIZE 7 /* retired: the aggregate kernel writes the result itself; never launched */
 #define SF_KERNEL_CORR_SIMT 8
 #define SF_KERNEL_UPSAMPLE 9
 SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
 /* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = v projection,
- * bit 1 = streaming GEMM, bit 2 = finalize) and sf_corr_build to (bit 0 = absmax + pack, bit 1 = GEMM), so bench.py
+ * bit 1 = streaming GEMM) and sf_corr_build to (bit 0 = absmax + pack, bit 1 = GEMM), so bench.py
  * can time one kernel back-to-back inside a CUDA graph.  Results are meaningless unless all bits are set (default). */
 SF_API void sf_debug_select_kernels(int gma_aggregate_mask, int corr_build_mask);
 
@@ -118,12 +118,15 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
  *     E[p,i,j]   = fp16(2^12 * exp(s_ij - max_j s_ij)),   s = (scale * q) . k,   [q; k] = W_qk . fmap
  *     rowsum[p,i] = sum_j E[p,i,j]                         (softmax = E / rowsum)
  * with E stored tile-major as [P][ceil(N/128)][Npad/64][128][64] fp16 (Npad = sf_gma_npad(N) = round_up(N, 64);
- * every 128-query x 64-key tile is one contiguous 16 KB block so the per-iteration stream reads whole DRAM
- * pages; pad key columns are zero; sf_gma_e_elems(P, N) is the element count to allocate), and
+ * every 128-query x 64-key tile is one contiguous 16 KB block holding the 128-byte-swizzled K-major image the
+ * tensor-core descriptor reads -- 16-byte chunk c of query row r sits at chunk c ^ (r & 7) of its 128-byte row --
+ * so any run of queries is one contiguous bulk copy; pad key columns are zero; sf_gma_e_elems(P, N) is the
+ * element count to allocate), and
  * sf_gma_aggregate computes every iteration
  *     out = fmap + gamma * ((E / rowsum) . (W_v . fmap)^T).
- * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) must be the SAME buffer for the attention call
- * and all aggregate calls that use its E: it holds the fp32 accumulation buffer the aggregate keeps zeroed. */
+ * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) is scratch for the projections; one buffer may serve
+ * the attention call and all aggregate calls on the same stream.  The aggregate is deterministic (one fp32
+ * accumulator per output element, no atomics). */
 SF_API int64_t sf_gma_npad(int64_t N);
 SF_API int64_t sf_gma_e_elems(int64_t P, int64_t N);
 SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);

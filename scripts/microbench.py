@@ -61,7 +61,16 @@ def graph_time(name, fn, n=12):
 
 graph_time("group lookup (3 pairs)", lambda i: group(coords[i % 12]))
 graph_time("single-pair lookup", lambda i: blocks[0](coords[i % 12][0]))
-graph_time("aggregate (proj+agg+finalize)", lambda i: agg(handle, t["mfs"]))
+graph_time("aggregate (proj + agg)", lambda i: agg(handle, t["mfs"]))
 graph_time("corr build (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4), n=6)
 graph_time("corr build f16x2 (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4, precision="f16x2"), n=6)
 graph_time("attention (3 maps)", lambda i: att(t["inps"]), n=3)
+
+L = _lib.lib() if hasattr(_lib, "lib") else None
+if L is not None:
+    for mask, name in ((1, "  v projection only"), (2, "  aggregate kernel only")):
+        L.sf_debug_select_kernels(mask, 3)
+        try:
+            graph_time(name, lambda i: agg(handle, t["mfs"]))
+        finally:
+            L.sf_debug_select_kernels(7, 3)

@@ -117,7 +117,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what) {
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, bool swizzle128) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -128,7 +128,8 @@ int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_
     const cuuint32_t box[3] = {b0, b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)", what,

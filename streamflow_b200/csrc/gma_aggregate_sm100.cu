@@ -1,23 +1,27 @@
-// G3b: per-iteration GMA aggregation (core/gma.py:91-104) as a streaming tcgen05 GEMM
+// G3b: per-iteration GMA aggregation (core/gma.py:91-104), one kernel, no split-K:
 //
-//     acc[p, c, n] += sum_j E[p, n, j] * V[p, c, j]          (gma_aggregate_kernel, this file)
-//     out[p, c, n]  = fmap[p, c, n] + acc[p, c, n] * gamma / rowsum[p, n];  acc <- 0     (gma_finalize_kernel)
+//     out[p, c, n] = fmap[p, c, n] + (gamma / rowsum[p, n]) * sum_j V[p, c, j] * E[p, n, j]
 //
-// HBM-bound on the fp16 softmax numerators E (297 MB per Sintel clip and iteration).  Design points:
-//   * one CTA owns TWO 128-query tiles (M = 256) per key block, so each 16 KB V tile fetched from L2 feeds two MMAs:
-//     SM ingest is 1.5 B per E byte instead of 2 -- with M = 128 the kernel sat on the L2->SM bandwidth cap
-//     (measured: ~10.4 TB/s of L2 reads for 4.9 TB/s of HBM), not on HBM;
-//   * stream-K: the linear (map, tile-pair, key-block) space is cut into gridDim equal contiguous ranges, so every SM
-//     streams the same number of bytes (165 tiles over 148 SMs would otherwise quantise to 2 waves);
-//   * E tiles are 16 KB contiguous blocks (tile-major layout written by gma_stats_kernel) on a deep mbarrier ring
-//     (5 x 32 KB in flight per SM), V on a shallow one (3 x 16 KB);
-//   * split tiles are reduced with red.global.add.f32 into a channel-major fp32 buffer: thread = query row, so for
-//     each channel the 32 lanes of a warp hit one 128 B line.  (A fused "last arriver" fix-up epilogue was tried
-//     and rejected: with in-order stream-K every CTA ends on a shared tile, so the 512 KB/tile fix-up traffic is
-//     issued by 128 threads at the very end of the kernel, latency-bound and fully exposed -- 159 us vs 62 us.)
+// HBM-bound on the fp16 softmax numerators E (297 MB per Sintel clip and iteration).  The GEMM is issued
+// TRANSPOSED -- D[channel, query] = V[channel, key] . E[query, key]^T, M = 128 channels, N = queries -- because the
+// UMMA N extent is any multiple of 16 up to 256: the query rows of all maps are cut into 16-row units and every CTA
+// owns one contiguous range of units (the same count +-1 everywhere), for ALL key blocks.  Consequences:
+//   * every SM streams the same number of E bytes without split-K: no fp32 scratch accumulator, no atomics, no
+//     memset, no separate finalize pass, and the result is deterministic (one fp32 accumulator per output);
+//   * the accumulator comes out of TMEM channel-major (lane = channel, column = query), which is the NCHW layout
+//     of the result: the epilogue fuses the residual add and the softmax normalisation and writes `out` directly;
+//   * E is tile-major: 16 KB blocks of 128 queries x 64 keys, each block stored by gma_stats_kernel as the
+//     128B-swizzled K-major shared-memory image the UMMA descriptor expects, so a run of queries inside a block is
+//     contiguous in HBM and lands with ONE non-tensor bulk copy (cp.async.bulk); a row range touches at most 3
+//     blocks.  (Fetching the same rows as power-of-two TMA boxes cost 4-9 TMA instructions per key block and ran
+//     at half the speed: per-instruction TMA cost, not bytes, was the limit.)
+// Memory-level parallelism is the whole game: the kernel is latency-bound until ~160 KB of E per SM are in flight
+// (measured: 108 KB in flight -> 4.4 TB/s, 160 KB -> 6 TB/s).  The E ring takes every byte of shared memory that
+// the 3-stage V ring (16 KB per key block, L2 resident, evict_last) leaves: 9 stages x 18 KB at Sintel size.
 //
-// warps: 0 = E producer (TMA), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-6 = epilogue.
+// warps: 0 = E producer (bulk copies), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-10 = epilogue.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "sf_internal.h"
 #include "sm100_ptx.cuh"
@@ -26,28 +30,104 @@ namespace sf {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kEStages = 5, kVStages = 3;
-constexpr int kTileBytes = BM * BK * 2;                          // 16 KB
-constexpr int kEStageBytes = 2 * kTileBytes;                     // two query tiles per stage
-constexpr int kSmemBytes = kEStages * kEStageBytes + kVStages * kTileBytes + 1024 + 512;
-constexpr int kTmemCols = 512;                                   // 2 buffers x (2 tiles x 128 columns)
-constexpr int kThreads = 224;
+constexpr int BK = 64, kCh = 128;
+constexpr int kUnit = 16;                                   // query rows per work unit (UMMA N granularity at M=128)
+constexpr int kMaxUnits = 16;                               // 256 rows = the UMMA N limit
+constexpr int kMaxEStages = 12, kVStages = 3;
+constexpr int kVBytes = kCh * BK * 2;                       // 16 KB
+constexpr int kSmemBytes = 227 * 1024;                      // everything the SM has
+constexpr int kBarBytes = 512;
+constexpr int kRing = (kSmemBytes - 1024 /*align slack*/ - kBarBytes) / 1024 * 1024;
+constexpr int kTmemCols = 512;                              // 2 accumulators x 256 columns
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (3 + kEpiWarps) * 32;
 
 struct GmaAggArgs {
-    CUtensorMap tm_e, tm_v;
+    CUtensorMap tm_v;
     GmaAggParams p;
+    int units_per_map;              // ceil(N / 16)
+    int e_stages, e_stage_bytes;    // E stage = the rows of the longest segment
+    int fbuf_pitch;                 // > 0: the fmap tile of the CTA's single segment is prefetched into shared memory
+    int fbuf_off, rbuf_off;         // byte offsets of that tile and of its rscale row inside the ring
 };
 
+struct Seg {
+    int pb, row0, rows;
+};
+
+// next run of units inside one map, at most 256 rows
+__device__ __forceinline__ bool next_seg(long long& u, long long u_end, int upm, Seg& s) {
+    if (u >= u_end) return false;
+    const int pb = static_cast<int>(u / upm);
+    const int ul = static_cast<int>(u - static_cast<long long>(pb) * upm);
+    const int n = min(min(kMaxUnits, upm - ul), static_cast<int>(u_end - u));
+    s.pb = pb;
+    s.row0 = ul * kUnit;
+    s.rows = n * kUnit;
+    u += n;
+    return true;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_chunk(const T* fm, const float* rs, int n0, int N, bool vec, float (&f)[16],
+                                           float (&r)[16]) {
+    if constexpr (sizeof(T) == 4) {
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (n0 + 4 * j < N) {
+                    a = *reinterpret_cast<const float4*>(fm + 4 * j);
+                    b = __ldg(reinterpret_cast<const float4*>(rs + 4 * j));
+                }
+                f[4 * j] = a.x; f[4 * j + 1] = a.y; f[4 * j + 2] = a.z; f[4 * j + 3] = a.w;
+                r[4 * j] = b.x; r[4 * j + 1] = b.y; r[4 * j + 2] = b.z; r[4 * j + 3] = b.w;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const bool ok = n0 + j < N;
+        f[j] = ok ? static_cast<float>(fm[j]) : 0.f;
+        r[j] = ok ? __ldg(rs + j) : 0.f;
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// out[n0 .. n0+16) = fmap + acc * rscale for one channel; `vec`: N % 4 == 0, so float4 stores never straddle N
+__device__ __forceinline__ void store_chunk(float* out, int n0, int N, bool vec, const uint32_t (&v)[16],
+                                            const float (&f)[16], const float (&r)[16]) {
+    if (vec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (n0 + 4 * j < N)
+                __stcs(reinterpret_cast<float4*>(out + n0 + 4 * j),
+                       make_float4(fmaf(__uint_as_float(v[4 * j]), r[4 * j], f[4 * j]),
+                                   fmaf(__uint_as_float(v[4 * j + 1]), r[4 * j + 1], f[4 * j + 1]),
+                                   fmaf(__uint_as_float(v[4 * j + 2]), r[4 * j + 2], f[4 * j + 2]),
+                                   fmaf(__uint_as_float(v[4 * j + 3]), r[4 * j + 3], f[4 * j + 3])));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (n0 + j < N) out[n0 + j] = fmaf(__uint_as_float(v[j]), r[j], f[j]);
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* e_base = smem;
-    uint8_t* v_base = smem + kEStages * kEStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v_base + kVStages * kTileBytes);
+    uint8_t* v_base = smem + kRing - kVStages * kVBytes;     // [E ring | fmap tile + rscale (optional) | V ring | barriers]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing);
     uint64_t* e_full = bars;
-    uint64_t* e_empty = e_full + kEStages;
-    uint64_t* v_full = e_empty + kEStages;
+    uint64_t* e_empty = e_full + kMaxEStages;
+    uint64_t* v_full = e_empty + kMaxEStages;
     uint64_t* v_empty = v_full + kVStages;
     uint64_t* tfull = v_empty + kVStages;
     uint64_t* tempty = tfull + 2;
@@ -55,16 +135,41 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
 
     const GmaAggParams& p = args.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long KB = p.k_blocks;
-    const long long G = gridDim.x;
-    const long long work = static_cast<long long>(p.P) * p.pair_tiles * KB;
-    const long long w_begin = work * blockIdx.x / G;
-    const long long w_end = work * (blockIdx.x + 1) / G;
+    const int KB = p.k_blocks;
+    const int upm = args.units_per_map;
+    const int e_stages = args.e_stages;
+    // Work split.  With at least one CTA per map, every map gets floor(G / P) or one more CTAs and each CTA a
+    // contiguous run of that map's units: no CTA straddles two maps (a straddler would run the key loop twice --
+    // twice the V traffic and iterations for the same E bytes -- and become the tail of the kernel).
+    long long u_begin, u_end;
+    {
+        const int G = gridDim.x, bid = blockIdx.x;
+        if (p.P <= G) {
+            const int base = G / p.P, extra = G % p.P;
+            int pb, j, g;
+            if (bid < extra * (base + 1)) {
+                pb = bid / (base + 1);
+                j = bid - pb * (base + 1);
+                g = base + 1;
+            } else {
+                const int b2 = bid - extra * (base + 1);
+                pb = extra + b2 / base;
+                j = b2 - (b2 / base) * base;
+                g = base;
+            }
+            const long long m0 = static_cast<long long>(pb) * upm;
+            u_begin = m0 + static_cast<long long>(upm) * j / g;
+            u_end = m0 + static_cast<long long>(upm) * (j + 1) / g;
+        } else {
+            const long long U = static_cast<long long>(p.P) * upm;
+            u_begin = U * bid / G;
+            u_end = U * (bid + 1) / G;
+        }
+    }
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&args.tm_e);
         tma_prefetch_desc(&args.tm_v);
-        for (int i = 0; i < kEStages; ++i) {
+        for (int i = 0; i < kMaxEStages; ++i) {
             mbar_init(&e_full[i], 1);
             mbar_init(&e_empty[i], 1);
         }
@@ -74,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], kEpiWarps);
         }
         fence_mbar_init();
     }
@@ -90,24 +195,34 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         if (lane == 0) {                                       // ---- E producer
             int stage = 0;
             uint32_t phase = 0;
-            for (long long pos = w_begin; pos < w_end; ++pos) {
-                const long long pt = pos / KB;
-                const int kb = static_cast<int>(pos - pt * KB);
-                const int pb = static_cast<int>(pt / p.pair_tiles);
-                const int mp = static_cast<int>(pt - static_cast<long long>(pb) * p.pair_tiles);
-                mbar_wait(&e_empty[stage], phase ^ 1);
-                uint8_t* dst = e_base + stage * kEStageBytes;
-                mbar_expect_tx(&e_full[stage], kEStageBytes);
-                // tile-major E: (m-tile, key-block) -> 128 consecutive 128-byte rows; a tile index past the last
-                // m-tile (odd tile count) is out of bounds for the tensor map and arrives as zeros
-                const long long r0 = (static_cast<long long>(2 * mp) * KB + kb) * BM;
-                const long long r1 = (static_cast<long long>(2 * mp + 1) * KB + kb) * BM;
-                tma_load_3d_hint(&args.tm_e, &e_full[stage], dst, 0, static_cast<int>(r0), pb, kEvictFirst);
-                tma_load_3d_hint(&args.tm_e, &e_full[stage], dst + kTileBytes, 0, static_cast<int>(r1), pb,
-                                 kEvictFirst);
-                if (++stage == kEStages) {
-                    stage = 0;
-                    phase ^= 1;
+            long long u = u_begin;
+            Seg s;
+            while (next_seg(u, u_end, upm, s)) {
+                // contiguous runs of the row range: one per 128-row block it touches (at most 3)
+                const int end = s.row0 + s.rows;
+                const int cut1 = min(end, (s.row0 | 127) + 1);
+                const int cut2 = min(end, cut1 + 128);
+                const __half* eb = p.e_ptr + static_cast<long long>(s.pb) * p.e_map_stride;
+                const __half* src0 = eb + (static_cast<long long>(s.row0 >> 7) * KB * 128 + (s.row0 & 127)) * 64;
+                const __half* src1 = eb + static_cast<long long>(cut1 >> 7) * KB * 128 * 64;
+                const __half* src2 = eb + static_cast<long long>(cut2 >> 7) * KB * 128 * 64;
+                const uint32_t bytes = static_cast<uint32_t>(s.rows) * 128u;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&e_empty[stage], phase ^ 1);
+                    uint8_t* dst = e_base + stage * args.e_stage_bytes;
+                    mbar_expect_tx(&e_full[stage], bytes);
+                    const long long blk = static_cast<long long>(kb) * 128 * 64;
+                    bulk_load_hint(dst, src0 + blk, (cut1 - s.row0) * 128, &e_full[stage], kEvictFirst);
+                    if (cut1 < end)
+                        bulk_load_hint(dst + (cut1 - s.row0) * 128, src1 + blk, (cut2 - cut1) * 128, &e_full[stage],
+                                       kEvictFirst);
+                    if (cut2 < end)
+                        bulk_load_hint(dst + (cut2 - s.row0) * 128, src2 + blk, (end - cut2) * 128, &e_full[stage],
+                                       kEvictFirst);
+                    if (++stage == e_stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -115,50 +230,44 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         if (lane == 0) {                                       // ---- V producer
             int stage = 0;
             uint32_t phase = 0;
-            for (long long pos = w_begin; pos < w_end; ++pos) {
-                const long long pt = pos / KB;
-                const int kb = static_cast<int>(pos - pt * KB);
-                const int pb = static_cast<int>(pt / p.pair_tiles);
-                mbar_wait(&v_empty[stage], phase ^ 1);
-                mbar_expect_tx(&v_full[stage], kTileBytes);
-                tma_load_3d_hint(&args.tm_v, &v_full[stage], v_base + stage * kTileBytes, kb * BK, 0, pb, kEvictLast);
-                if (++stage == kVStages) {
-                    stage = 0;
-                    phase ^= 1;
+            long long u = u_begin;
+            Seg s;
+            while (next_seg(u, u_end, upm, s)) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(&v_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&v_full[stage], kVBytes);
+                    tma_load_3d_hint(&args.tm_v, &v_full[stage], v_base + stage * kVBytes, kb * BK, 0, s.pb,
+                                     kEvictLast);
+                    if (++stage == kVStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                       // ---- MMA issuer
-            constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
             int es = 0, vs = 0, local = 0;
             uint32_t ephase = 0, vphase = 0;
-            long long pos = w_begin;
-            while (pos < w_end) {
-                const long long pt = pos / KB;
-                const long long seg_end = min(w_end, (pt + 1) * KB);
+            long long u = u_begin;
+            Seg s;
+            while (next_seg(u, u_end, upm, s)) {
                 const int acc = local & 1;
                 mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (2 * BN);
-                bool first = true;
-                for (; pos < seg_end; ++pos) {
+                const uint32_t idesc = make_idesc_f16_f32(kCh, s.rows);
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&v_full[vs], vphase);
                     mbar_wait(&e_full[es], ephase);
                     tc_fence_after();
-                    const uint32_t ea = smem_u32(e_base + es * kEStageBytes);
-                    const uint64_t d0 = make_kmajor_sw128_desc(ea);
-                    const uint64_t d1 = make_kmajor_sw128_desc(ea + kTileBytes);
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(v_base + vs * kTileBytes));
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(v_base + vs * kVBytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(e_base + es * args.e_stage_bytes));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_f16_ss(d_tmem, d0 + 2 * k, db + 2 * k, idesc, !(first && k == 0));
-                        umma_f16_ss(d_tmem + BN, d1 + 2 * k, db + 2 * k, idesc, !(first && k == 0));
-                    }
-                    first = false;
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(&e_empty[es]);
                     umma_commit(&v_empty[vs]);
-                    if (++es == kEStages) {
+                    if (++es == e_stages) {
                         es = 0;
                         ephase ^= 1;
                     }
@@ -171,46 +280,105 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
                 ++local;
             }
         }
-    } else {                                                   // ---- epilogue (warps 3-6)
-        const int quad = warp & 3;
+    } else {                                                   // ---- epilogue (warps 3-10)
+        const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
+        const int sub = (warp - 3) >> 2;                       // which half of the 16-column chunks
+        const int ch = quad * 32 + lane;                       // channel = TMEM lane
         int local = 0;
-        long long pos = w_begin;
-        while (pos < w_end) {
-            const long long pt = pos / KB;
-            const long long seg_end = min(w_end, (pt + 1) * KB);
-            const int pb = static_cast<int>(pt / p.pair_tiles);
-            const int mp = static_cast<int>(pt - static_cast<long long>(pb) * p.pair_tiles);
+        long long u = u_begin;
+        Seg s;
+        if (args.fbuf_pitch > 0) {
+            // Single-segment CTA: the epilogue is the un-overlapped tail of the kernel, so everything it reads from
+            // global memory (the fmap tile, its rscale row) is fetched into shared memory while the key loop runs.
+            if (next_seg(u, u_end, upm, s)) {
+                uint8_t* fbuf = smem + args.fbuf_off;
+                float* rbuf = reinterpret_cast<float*>(smem + args.rbuf_off);
+                const int t = threadIdx.x - 96;
+                const int valid = min(s.rows, p.N - s.row0);
+                const int cpr = valid * static_cast<int>(sizeof(T)) / 16;         // 16-byte chunks per channel row
+                const T* fm0 = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(s.pb) * kCh * p.N + s.row0;
+                for (int i = t; i < kCh * cpr; i += kEpiWarps * 32) {
+                    const int c = i / cpr, k = i - c * cpr;
+                    cp_async16(fbuf + c * args.fbuf_pitch + k * 16,
+                               reinterpret_cast<const uint8_t*>(fm0 + static_cast<long long>(c) * p.N) + k * 16);
+                }
+                const float* rs = p.rscale + static_cast<long long>(s.pb) * p.N + s.row0;
+                for (int i = t; i < valid / 4; i += kEpiWarps * 32) cp_async16(rbuf + 4 * i, rs + 4 * i);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+
+                float* out = p.out + (static_cast<long long>(s.pb) * kCh + ch) * p.N;
+                const uint8_t* frow = fbuf + ch * args.fbuf_pitch;
+                const int chunks = s.rows / 16;
+                mbar_wait(&tfull[0], 0);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+                for (int c = sub; c < chunks; c += 2) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_acc + c * 16, v);
+                    float f[16], r[16];
+                    if (c * 16 < valid) {      // chunks past N are never stored
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b = *reinterpret_cast<const float4*>(rbuf + c * 16 + 4 * j);
+                            r[4 * j] = b.x; r[4 * j + 1] = b.y; r[4 * j + 2] = b.z; r[4 * j + 3] = b.w;
+                        }
+                        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = *reinterpret_cast<const float4*>(frow + c * 64 + 16 * j);
+                                f[4 * j] = a.x; f[4 * j + 1] = a.y; f[4 * j + 2] = a.z; f[4 * j + 3] = a.w;
+                            }
+                        } else {
+                            alignas(16) T h[16];
+                            *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(frow + c * 32);
+                            *reinterpret_cast<uint4*>(h + 8) = *reinterpret_cast<const uint4*>(frow + c * 32 + 16);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = static_cast<float>(h[j]);
+                        }
+                    }
+                    tmem_ld_wait();
+                    store_chunk(out, s.row0 + c * 16, p.N, true, v, f, r);
+                }
+            }
+        } else {
+        const bool vec = (p.N & 3) == 0;
+        while (next_seg(u, u_end, upm, s)) {
             const int acc = local & 1;
+            const int chunks = s.rows / 16;
+            const long long base = (static_cast<long long>(s.pb) * kCh + ch) * p.N;
+            const T* fm = reinterpret_cast<const T*>(p.fmap) + base;
+            const float* rs = p.rscale + static_cast<long long>(s.pb) * p.N;
+            float* out = p.out + base;
+            float f[16], r[16];
+            if (sub < chunks) load_chunk<T>(fm + s.row0 + sub * 16, rs + s.row0 + sub * 16, s.row0 + sub * 16, p.N, vec, f, r);
             mbar_wait(&tfull[acc], (local >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (2 * BN);
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int n = (2 * mp + half) * BM + quad * 32 + lane;
-                // acc is channel-major [P, 128, N] (the layout of the NCHW result): for a fixed channel the 32
-                // lanes of a warp hit 32 consecutive floats, so every warp-level red is one coalesced 128 B line
-                float* dst = p.acc + static_cast<long long>(pb) * BN * p.N + n;
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_acc + half * BN + ch * 32, v);
-                    tmem_ld_wait();
-                    if (half == 1 && ch == BN / 32 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);
-                    }
-                    if (n < p.N) {
+            for (int c = sub; c < chunks; c += 2) {
+                uint32_t v[16];
+                tmem_ld_32x16(t_acc + c * 16, v);
+                float fn[16], rn[16];
+                const int n0 = s.row0 + c * 16;
+                if (c + 2 < chunks) load_chunk<T>(fm + n0 + 32, rs + n0 + 32, n0 + 32, p.N, vec, fn, rn);
+                tmem_ld_wait();
+                store_chunk(out, n0, p.N, vec, v, f, r);
+                if (c + 2 < chunks) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + static_cast<long long>(ch * 32 + j) * p.N),
-                                         "f"(__uint_as_float(v[j]))
-                                         : "memory");
+                    for (int j = 0; j < 16; ++j) {
+                        f[j] = fn[j];
+                        r[j] = rn[j];
                     }
                 }
             }
-            pos = seg_end;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
             ++local;
+        }
         }
     }
 
@@ -222,70 +390,50 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     }
 }
 
-// out[p, c, n] = fmap[p, c, n] + acc[p, c, n] * (gamma / rowsum[p, n]);  acc <- 0.
-// grid = (ceil(N / 1024), P * C): one float4 per thread, no index arithmetic, every load in flight at once.
 template <typename T>
-__global__ void __launch_bounds__(256) gma_finalize_kernel(const __grid_constant__ GmaAggParams p) {
-    pdl_launch();
-    pdl_wait();
-    const int row = blockIdx.y;                          // p * C + c
-    const int pb = row / p.C;
-    const long long base = static_cast<long long>(row) * p.N;
-    const T* fm = reinterpret_cast<const T*>(p.fmap) + base;
-    float* acc = p.acc + base;
-    float* out = p.out + base;
-    const float* rs = p.rscale + static_cast<long long>(pb) * p.N;
-    const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (n >= p.N) return;
-    if ((p.N & 3) == 0) {
-        const float4 a = *reinterpret_cast<const float4*>(acc + n);
-        const float4 r = __ldg(reinterpret_cast<const float4*>(rs + n));
-        const float f0 = static_cast<float>(fm[n]), f1 = static_cast<float>(fm[n + 1]);
-        const float f2 = static_cast<float>(fm[n + 2]), f3 = static_cast<float>(fm[n + 3]);
-        *reinterpret_cast<float4*>(acc + n) = make_float4(0.f, 0.f, 0.f, 0.f);
-        __stcs(reinterpret_cast<float4*>(out + n),
-               make_float4(fmaf(a.x, r.x, f0), fmaf(a.y, r.y, f1), fmaf(a.z, r.z, f2), fmaf(a.w, r.w, f3)));
-    } else {
-        for (int e = n; e < min(n + 4, p.N); ++e) {
-            const float a = acc[e];
-            acc[e] = 0.f;
-            out[e] = fmaf(a, __ldg(rs + e), static_cast<float>(fm[e]));
-        }
-    }
-}
-
-}  // namespace
-
-int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
-                         cudaStream_t s) {
-    GmaAggArgs args;
-    args.tm_e = tm_e;
-    args.tm_v = tm_v;
-    args.p = p;
-    const long long work = static_cast<long long>(p.P) * p.pair_tiles * p.k_blocks;
-    const int grid = static_cast<int>(std::min<long long>(work, num_sms));
-    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+int launch_typed(const GmaAggArgs& args, int grid, cudaStream_t s) {
+    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_aggregate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemBytes));
     prof_before(SF_KERNEL_GMA_AGGREGATE, s);
-    SF_CUDA_CHECK(launch_kernel(gma_aggregate_kernel, dim3(grid), dim3(kThreads), kSmemBytes, s, args));
+    SF_CUDA_CHECK(launch_kernel(gma_aggregate_kernel<T>, dim3(grid), dim3(kThreads), kSmemBytes, s, args));
     prof_after(SF_KERNEL_GMA_AGGREGATE, s);
     SF_CUDA_CHECK(cudaGetLastError());
     return SF_OK;
 }
 
-int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s) {
-    dim3 grid((p.N + 1023) / 1024, p.P * p.C);
-    prof_before(SF_KERNEL_GMA_FINALIZE, s);
-    switch (p.fmap_dtype) {
-        case SF_DT_F32: SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<float>, grid, dim3(256), 0, s, p)); break;
-        case SF_DT_F16: SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<__half>, grid, dim3(256), 0, s, p)); break;
-        case SF_DT_BF16:
-            SF_CUDA_CHECK(launch_kernel(gma_finalize_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, p));
-            break;
-        default: set_error("gma_finalize: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
+}  // namespace
+
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num_sms, cudaStream_t s) {
+    GmaAggArgs args;
+    args.tm_v = tm_v;
+    args.p = p;
+    args.units_per_map = (p.N + kUnit - 1) / kUnit;
+    const long long U = static_cast<long long>(p.P) * args.units_per_map;
+    const int grid = static_cast<int>(std::min<long long>(U, num_sms));
+    const long long per_cta = (p.P <= grid) ? (args.units_per_map + grid / p.P - 1) / (grid / p.P) : (U + grid - 1) / grid;
+    const int seg_units = static_cast<int>(std::min<long long>(kMaxUnits, per_cta));
+    args.e_stage_bytes = seg_units * kUnit * 128;
+    const int elt = (p.fmap_dtype == SF_DT_F32) ? 4 : 2;
+    const int rows_cap = seg_units * kUnit;
+    int avail = kRing - kVStages * kVBytes;
+    // staged epilogue: one segment per CTA, 16-byte aligned fmap rows, and room for at least 4 E stages next to the tile
+    args.fbuf_pitch = 0;
+    args.fbuf_off = args.rbuf_off = 0;
+    const int fbuf_bytes = (kCh * (rows_cap * elt + 16) + rows_cap * 4 + 1023) / 1024 * 1024;
+    if (per_cta <= kMaxUnits && (static_cast<long long>(p.N) * elt) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(p.fmap) & 15) == 0 && avail - fbuf_bytes >= 4 * args.e_stage_bytes) {
+        args.fbuf_pitch = rows_cap * elt + 16;
+        avail -= fbuf_bytes;
+        args.fbuf_off = avail;
+        args.rbuf_off = avail + kCh * args.fbuf_pitch;
     }
-    prof_after(SF_KERNEL_GMA_FINALIZE, s);
-    SF_CUDA_CHECK(cudaGetLastError());
-    return SF_OK;
+    args.e_stages = std::min(kMaxEStages, avail / args.e_stage_bytes);
+    switch (p.fmap_dtype) {
+        case SF_DT_F32: return launch_typed<float>(args, grid, s);
+        case SF_DT_F16: return launch_typed<__half>(args, grid, s);
+        case SF_DT_BF16: return launch_typed<__nv_bfloat16>(args, grid, s);
+        default: set_error("gma_aggregate: unsupported dtype %d", p.fmap_dtype); return SF_ERR_INVALID;
+    }
 }
 
 }  // namespace sf

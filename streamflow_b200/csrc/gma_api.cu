@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, v_off, acc_off, rscale_off, total;
+    int64_t q_off, k_off, rowmax_off, v_off, rscale_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -19,7 +19,6 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.k_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
     ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
-    ws.acc_off = off;     off += align_up(P * N * d * 4, 1024);
     ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
     ws.total = off;
     return ws;
@@ -88,7 +87,6 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
 
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
     SF_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, P * N * 4, s));
-    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.acc_off, 0, P * N * d * 4, s));
 
     CUtensorMap tm_q, tm_k, tm_e;
     const uint64_t kp = static_cast<uint64_t>(Kp);
@@ -100,8 +98,9 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
         return rc;
     // E is tile-major [P][m_tiles][Npad/64][128][64]: a 2-D view of 128-byte rows per map
     const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
+    // no TMA swizzle on the store: HBM keeps the swizzled shared-memory image of every 16 KB block
     if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 32,
-                            "E(store)"))
+                            "E(store)", /*swizzle128=*/false))
         return rc;
 
     GmaStatsParams sp{};
@@ -146,27 +145,21 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     if (parts & 1)
         if (int rc = (w_dtype == SF_DT_F16) ? launch_gma_proj_v(pv, s) : launch_gma_proj(pv, s)) return rc;
 
-    CUtensorMap tm_e, tm_v;
-    const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
-    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 128,
-                            "E(load)"))
-        return rc;
+    CUtensorMap tm_v;
+    const int64_t e_rows = (N + 127) / 128 * (Npad / 64) * 128;       // 128-byte rows of tile-major E per map
     if (int rc = make_tmap3(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.v_off, Npad, d, P, Npad * 2,
                             d * Npad * 2, 64, 128, "V"))
         return rc;
 
     GmaAggParams ap{};
     ap.P = (int)P; ap.N = (int)N; ap.Npad = (int)Npad; ap.C = (int)C;
-    ap.m_tiles = (int)((N + 127) / 128);
-    ap.pair_tiles = (ap.m_tiles + 1) / 2;
     ap.k_blocks = (int)(Npad / 64);
-    ap.acc = reinterpret_cast<float*>(wsb + ws.acc_off);
     ap.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
     ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
     ap.out = out;
-    if (parts & 2)
-        if (int rc = launch_gma_aggregate(ap, tm_e, tm_v, di.sms, s)) return rc;
-    return (parts & 4) ? launch_gma_finalize(ap, s) : SF_OK;
+    ap.e_ptr = static_cast<const __half*>(E);
+    ap.e_map_stride = e_rows * 64;
+    return (parts & 2) ? launch_gma_aggregate(ap, tm_v, di.sms, s) : SF_OK;
 }
 
 }  // extern "C"

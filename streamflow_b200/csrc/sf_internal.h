@@ -82,7 +82,7 @@ struct DeviceInfo {
 int query_device(DeviceInfo* out);
 // rank-3 tiled TMA map, 128B swizzle: dims / box innermost first; strides (bytes) of dims 1 and 2; box[2] = 1.
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what);
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, bool swizzle128 = true);
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // Power-of-two operand scale derived from a tensor's absmax (bits of a non-negative float):
@@ -162,7 +162,7 @@ struct GmaProjParams {
     int token_major;
     int split;            // token-major only: also write lo/hi split parts at column offsets O and 2*O
     int is_b;
-    // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the finalize kernel,
+    // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the aggregate epilogue,
     // so that no later kernel has thousands of warps reading the single gamma word
     const float* rowsum;
     const float* gamma;
@@ -186,17 +186,15 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
 
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
-    int m_tiles, pair_tiles;    // ceil(N/128), ceil(m_tiles/2): one CTA work item covers two query tiles
     int k_blocks;               // Npad / 64
-    float* acc;                 // [P, 128, N] fp32 accumulation buffer (zero on entry, re-zeroed by finalize)
     const float* rscale;        // [P, N] gamma / rowsum (written by the v projection)
     const void* fmap;           // [P, C, N]
     int fmap_dtype;
     float* out;                 // [P, C, N]
+    const __half* e_ptr;        // tile-major E (swizzled 16 KB blocks) and its per-map stride in elements
+    long long e_map_stride;
 };
-int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_e, const CUtensorMap& tm_v, int num_sms,
-                         cudaStream_t s);
-int launch_gma_finalize(const GmaAggParams& p, cudaStream_t s);
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num_sms, cudaStream_t s);
 int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
 
 int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,

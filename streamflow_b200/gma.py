@@ -44,7 +44,13 @@ class AttentionHandle:
         """Reference-shaped softmax matrix [P, 1, N, N] fp32 (test helper; O(N^2) memory)."""
         P, N = self.P, self.N
         mt, npad = (N + 127) // 128, self.E.numel() // (P * ((N + 127) // 128) * 128)
-        e = self.E.view(P, mt, npad // 64, 128, 64).permute(0, 1, 3, 2, 4).reshape(P, mt * 128, npad)
+        # every 16 KB block is the 128B-swizzled image: logical 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+        blocks = self.E.view(P, mt, npad // 64, 128, 8, 8)
+        r = torch.arange(128, device=self.E.device)[:, None]
+        c = torch.arange(8, device=self.E.device)[None, :]
+        idx = (c ^ (r & 7)).view(1, 1, 1, 128, 8, 1).expand_as(blocks)
+        e = blocks.gather(4, idx).reshape(P, mt, npad // 64, 128, 64)
+        e = e.permute(0, 1, 3, 2, 4).reshape(P, mt * 128, npad)
         return (e[:, :N, :N].float() / self.rowsum[:, :, None])[:, None]
 
     def row_sums_of_e(self):
