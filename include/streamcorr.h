@@ -140,6 +140,15 @@ SF_API int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk,
                      int64_t d, float scale, int precision, void* E, float* rowsum, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* The authors' memory-saving call convention (demo.py:235-282, test_memory.py:240-282): Attention.forward returns
+ * the projected (q, k) and Aggregate.forward(q, k, fmap) redoes the attention every iteration with
+ * flash_attn_func(q, k, v, softmax_scale = dim_head^-0.5).  q, k: [P, d, N] (NCHW flattened, contiguous) of dtype
+ * qk_dtype, NOT pre-scaled.  Produces the same E / rowsum as sf_gma_attention would from the fmap they were
+ * projected from; the caller caches them for as long as q and k are unchanged.                              */
+SF_API int sf_gma_attention_qk(const void* q, const void* k, int qk_dtype, int64_t P, int64_t N, int64_t d, float scale,
+                        int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
 /* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] of dtype w_dtype (SF_DT_F32, or SF_DT_F16 = weights the
  * caller converted once: the faster path, the projection rounds them to fp16 anyway); gamma: DEVICE pointer to
  * 1 float (no host sync); out: [P, C, N] fp32 (requires C == d: the reference's `project` is None,

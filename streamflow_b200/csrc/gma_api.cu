@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, v_off, rscale_off, total;
+    int64_t q_off, k_off, rowmax_off, v_off, rscale_off, eye_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -20,6 +20,7 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
     ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
     ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
+    ws.eye_off = off;     off += align_up(d * d * 4, 1024);
     ws.total = off;
     return ws;
 }
@@ -42,46 +43,26 @@ int check_gma(int64_t P, int64_t C, int64_t N, int64_t d, const void* ws, int64_
 }  // namespace
 }  // namespace sf
 
-using namespace sf;
+namespace sf {
+namespace {
 
-extern "C" {
-
-int64_t sf_gma_npad(int64_t N) { return align_up(N, 64); }
-
-int64_t sf_gma_e_elems(int64_t P, int64_t N) { return P * align_up(N, 128) * align_up(N, 64); }
-
-int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d) {
-    (void)C;
-    if (P < 1 || N < 1 || d < 1) return 0;
-    return gma_ws_layout(P, N, d).total;
-}
-
-int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N, int64_t d,
-                     float scale, int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
-                     void* stream) {
-    DeviceInfo di;
-    if (int rc = query_device(&di)) return rc;
-    const GmaWs ws = gma_ws_layout(P, N, d);
-    if (int rc = check_gma(P, C, N, d, workspace, workspace_bytes, ws)) return rc;
-    SF_REQUIRE(fmap && w_qk && E && rowsum, "gma_attention: null pointer argument");
-    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2, "gma_attention: unknown precision mode %d",
-               precision);
+// E, rowsum from  q = scale * W_q . xq,  k = W_k . xk  (xq == xk == fmap for the reference's Attention)
+int attention_common(const void* xq, const void* xk, int x_dtype, const float* w_q, const float* w_k, int64_t P,
+                     int64_t C, int64_t N, int64_t d, float scale, int precision, void* E, float* rowsum,
+                     uint8_t* wsb, const GmaWs& ws, const DeviceInfo& di, cudaStream_t s) {
     const int split = (precision == SF_PREC_F16X2);
     const int Kp = split ? ws.Kp : static_cast<int>(d);
-    SF_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0, "gma_attention: E must be 16-byte aligned");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    uint8_t* wsb = static_cast<uint8_t*>(workspace);
     const int64_t Npad = ws.Npad;
 
     GmaProjParams pq{};
-    pq.x = fmap; pq.x_dtype = fmap_dtype; pq.w = w_qk;
+    pq.x = xq; pq.x_dtype = x_dtype; pq.w = w_q;
     pq.P = (int)P; pq.C = (int)C; pq.N = (int)N; pq.O = 128;
     pq.scale = scale;
     pq.out = reinterpret_cast<__half*>(wsb + ws.q_off);
     pq.out_batch_stride = N * Kp; pq.ld = Kp; pq.token_major = 1; pq.split = split; pq.is_b = 0;
     if (int rc = launch_gma_proj(pq, s)) return rc;
     GmaProjParams pk = pq;
-    pk.w = w_qk + d * C; pk.scale = 1.0f;
+    pk.x = xk; pk.w = w_k; pk.scale = 1.0f;
     pk.out = reinterpret_cast<__half*>(wsb + ws.k_off); pk.is_b = 1;
     if (int rc = launch_gma_proj(pk, s)) return rc;
 
@@ -117,6 +98,57 @@ int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_
     if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
     sp.pass = 2;
     return launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s);
+}
+
+}  // namespace
+}  // namespace sf
+
+using namespace sf;
+
+extern "C" {
+
+int64_t sf_gma_npad(int64_t N) { return align_up(N, 64); }
+
+int64_t sf_gma_e_elems(int64_t P, int64_t N) { return P * align_up(N, 128) * align_up(N, 64); }
+
+int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d) {
+    (void)C;
+    if (P < 1 || N < 1 || d < 1) return 0;
+    return gma_ws_layout(P, N, d).total;
+}
+
+int sf_gma_attention(const void* fmap, int fmap_dtype, const float* w_qk, int64_t P, int64_t C, int64_t N, int64_t d,
+                     float scale, int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    const GmaWs ws = gma_ws_layout(P, N, d);
+    if (int rc = check_gma(P, C, N, d, workspace, workspace_bytes, ws)) return rc;
+    SF_REQUIRE(fmap && w_qk && E && rowsum, "gma_attention: null pointer argument");
+    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2, "gma_attention: unknown precision mode %d",
+               precision);
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0, "gma_attention: E must be 16-byte aligned");
+    return attention_common(fmap, fmap, fmap_dtype, w_qk, w_qk + d * C, P, C, N, d, scale, precision, E, rowsum,
+                            static_cast<uint8_t*>(workspace), ws, di, static_cast<cudaStream_t>(stream));
+}
+
+int sf_gma_attention_qk(const void* q, const void* k, int qk_dtype, int64_t P, int64_t N, int64_t d, float scale,
+                        int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    const GmaWs ws = gma_ws_layout(P, N, d);
+    if (int rc = check_gma(P, d, N, d, workspace, workspace_bytes, ws)) return rc;
+    SF_REQUIRE(q && k && E && rowsum, "gma_attention_qk: null pointer argument");
+    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2, "gma_attention_qk: unknown precision mode %d",
+               precision);
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0, "gma_attention_qk: E must be 16-byte aligned");
+    // q and k arrive already projected: run them through the same packing kernel with identity weights
+    uint8_t* wsb = static_cast<uint8_t*>(workspace);
+    float* eye = reinterpret_cast<float*>(wsb + ws.eye_off);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = launch_gma_identity(eye, static_cast<int>(d), s)) return rc;
+    return attention_common(q, k, qk_dtype, eye, eye, P, d, N, d, scale, precision, E, rowsum, wsb, ws, di, s);
 }
 
 int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,

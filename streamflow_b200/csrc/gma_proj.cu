@@ -376,4 +376,19 @@ int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s) {
     }
 }
 
+namespace {
+__global__ void gma_identity_kernel(float* dst, int d) {
+    pdl_launch();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d * d) dst[i] = (i / d == i % d) ? 1.0f : 0.0f;
+}
+}  // namespace
+
+int launch_gma_identity(float* dst, int d, cudaStream_t s) {
+    SF_CUDA_CHECK(launch_kernel(gma_identity_kernel, dim3((d * d + 255) / 256), dim3(256), 0, s, dst, d));
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
+
 }  // namespace sf

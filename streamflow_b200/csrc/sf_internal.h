@@ -195,7 +195,7 @@ struct GmaAggParams {
     long long e_map_stride;
 };
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num_sms, cudaStream_t s);
-int launch_fill_u32(unsigned* ptr, unsigned value, long long n, cudaStream_t s);
+int launch_gma_identity(float* dst, int d, cudaStream_t s);      // dst[d, d] <- I
 
 int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
                          int64_t W, cudaStream_t s);

@@ -11,6 +11,12 @@ reference checkpoints load unchanged (``to_qk.weight [2*inner, dim, 1, 1]``, ``t
 (the callers only pass it on to ``Aggregate``): it owns the fp16 softmax numerators E, their row sums and the
 workspace.  ``handle.dense()`` materialises the reference-shaped matrix for tests.
 
+The authors' memory-saving convention (``demo.py:235-282``, ``test_memory.py:240-282``) is accepted too:
+``Attention(..., return_qk=True)`` returns the projected ``(q, k)`` like their ``Attention`` and
+``Aggregate.forward(q, k, fmap)`` takes them in place of the handle.  Where the reference then redoes the whole
+attention with ``flash_attn_func`` every refinement iteration, this module builds E once per distinct (q, k) pair
+and reuses it for as long as the same, unmodified tensors come back.
+
 The kernels are specialised for the shipped configuration heads=1, dim=dim_head=128; anything else raises
 (there is no eager fallback).
 """
@@ -92,9 +98,10 @@ class Attention(nn.Module):
     "f16" rounds q, k to fp16 for the logit GEMM -- the operand precision of the reference's own autocast path, 7e-4
     vs the fp32 oracle, and 4 % faster on the whole step."""
 
-    def __init__(self, *, args, dim, max_pos_size=100, heads=4, dim_head=128):
+    def __init__(self, *, args, dim, max_pos_size=100, heads=4, dim_head=128, return_qk=False):
         super().__init__()
         self.precision = _GMA_PRECISION
+        self.return_qk = return_qk
         self.args = args
         self.heads = heads
         self.dim = dim
@@ -107,6 +114,10 @@ class Attention(nn.Module):
         _check_cfg(self.dim, self.heads, self.dim_head)
         if fmap.dim() != 4 or fmap.shape[1] != self.dim:
             raise StreamCorrError(f"Attention expects [P, {self.dim}, h, w], got {tuple(fmap.shape)}")
+        if self.return_qk:
+            # demo.py:268-273: the projection only; the attention itself happens inside Aggregate.forward(q, k, fmap)
+            q, k = self.to_qk(fmap).chunk(2, dim=1)
+            return q, k
         if self.precision not in ("f16", "f16x2"):
             raise StreamCorrError(f"unknown GMA precision {self.precision!r}; choose 'f16' or 'f16x2'")
         if not fmap.is_cuda:
@@ -142,6 +153,7 @@ class Aggregate(nn.Module):
         self.dim_head = dim_head
         self.scale = dim_head ** -0.5
         inner_dim = heads * dim_head
+        self.precision = _GMA_PRECISION          # used by the (q, k, fmap) convention only
         self.to_v = nn.Conv2d(dim, inner_dim, 1, bias=False)
         self.gamma = nn.Parameter(torch.zeros(1))
         if dim != inner_dim:
@@ -149,8 +161,45 @@ class Aggregate(nn.Module):
         else:
             self.project = None
 
-    def forward(self, attn, fmap):
+    def _handle_from_qk(self, q, k):
+        """E / rowsum for already-projected q, k [P, dim_head, h, w]; cached while the same tensors come back."""
+        if q.shape != k.shape or q.dim() != 4 or q.shape[1] != self.dim_head:
+            raise StreamCorrError(f"Aggregate(q, k, fmap) expects q, k of shape [P, {self.dim_head}, h, w], got "
+                                  f"{tuple(q.shape)} and {tuple(k.shape)}")
+        if not q.is_cuda or q.device != k.device or q.dtype != k.dtype:
+            raise StreamCorrError("Aggregate(q, k, fmap) needs q and k on the same CUDA device with the same dtype")
+        key = (q.data_ptr(), k.data_ptr(), q._version, k._version, tuple(q.shape), q.dtype, q.device, self.precision)
+        cached = getattr(self, "_qk_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[2]
+        qc, kc = q.detach().contiguous(), k.detach().contiguous()
+        P, d, h, w = qc.shape
+        N = h * w
+        dev = qc.device
+        L = _lib.lib()
+        with _on_device(dev):
+            E = torch.empty((L.sf_gma_e_elems(P, N),), dtype=torch.float16, device=dev)
+            rowsum = torch.empty((P, N), dtype=torch.float32, device=dev)
+            ws_bytes = L.sf_gma_workspace_bytes(P, d, N, d)
+            ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
+            rc = L.sf_gma_attention_qk(qc.data_ptr(), kc.data_ptr(), _lib.torch_dtype_code(qc.dtype), P, N, d,
+                                       float(self.scale), _lib.PRECISIONS[self.precision], E.data_ptr(),
+                                       rowsum.data_ptr(), ws_ptr, ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "sf_gma_attention_qk")
+        handle = AttentionHandle(E, rowsum, ws_buf, ws_ptr, ws_bytes, (P, d, h, w))
+        # the cache holds q and k so their storage cannot be recycled under the key
+        object.__setattr__(self, "_qk_cache", (key, (q, k), handle))
+        return handle
+
+    def forward(self, *inputs):
+        """``forward(attn, fmap)`` (core/gma.py:91) or ``forward(querys, keys, fmap)`` (demo.py:237)."""
         _check_cfg(self.dim, self.heads, self.dim_head)
+        if len(inputs) == 3:
+            attn, fmap = self._handle_from_qk(inputs[0], inputs[1]), inputs[2]
+        elif len(inputs) == 2:
+            attn, fmap = inputs
+        else:
+            raise TypeError(f"Aggregate.forward takes (attn, fmap) or (querys, keys, fmap), got {len(inputs)} arguments")
         if not isinstance(attn, AttentionHandle):
             raise StreamCorrError("Aggregate expects the handle returned by streamflow_b200.gma.Attention")
         if fmap.dim() != 4 or tuple(fmap.shape) != (attn.P, self.dim, attn.h, attn.w):

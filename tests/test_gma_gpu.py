@@ -139,3 +139,47 @@ def test_error_behaviour():
     agg = Aggregate(args=_Args(), dim=128, heads=1, dim_head=128).cuda()
     with pytest.raises(StreamCorrError):
         agg(torch.zeros(1, 1, 64, 64, device="cuda"), torch.zeros(1, 128, 8, 8, device="cuda"))
+
+
+@pytest.mark.parametrize("qk_dtype", [torch.float32, torch.float16])
+def test_qk_call_convention_matches_handle_convention(qk_dtype):
+    """Aggregate(querys, keys, fmap) -- the authors' flash-attention convention (demo.py:235-282) -- gives the
+    golden result of the reference's Attention + Aggregate, and reuses E while the same q, k come back."""
+    from streamflow_b200 import Aggregate, Attention
+    g = load_golden("gma_small.npz")
+    att = Attention(args=_Args(), dim=128, heads=1, max_pos_size=160, dim_head=128, return_qk=True).cuda()
+    agg = Aggregate(args=_Args(), dim=128, heads=1, dim_head=128).cuda()
+    with torch.no_grad():
+        att.to_qk.weight.copy_(cuda(g["w_qk"]).view(256, 128, 1, 1))
+        agg.to_v.weight.copy_(cuda(g["w_v"]).view(128, 128, 1, 1))
+        agg.gamma.fill_(float(g["gamma"]))
+        q, k = att(cuda(g["inp"]))
+        assert q.shape == k.shape == (g["inp"].shape[0], 128) + g["inp"].shape[2:]
+        q, k = q.to(qk_dtype), k.to(qk_dtype)
+        mf = cuda(g["mf"])
+        out = agg(q, k, mf)
+        handle = agg._qk_cache[2]
+        out2 = agg(q, k, mf)                       # second iteration: same tensors -> cached E
+        assert agg._qk_cache[2] is handle
+        torch.testing.assert_close(out, out2, rtol=0, atol=0)
+        q2 = q.clone()
+        agg(q2, k, mf)                             # a different q tensor -> rebuilt
+        assert agg._qk_cache[2] is not handle
+    out = out.cpu().numpy()
+    tol = 1e-3 if qk_dtype == torch.float32 else 3e-3       # fp16 q, k carry the reference's own autocast rounding
+    e_delta = rel_err(out - g["mf"], g["out"] - g["mf"])
+    assert e_delta < tol, f"gamma * attn.v rel err {e_delta:.3e}"
+    assert rel_err(out, g["out"]) < tol / 3
+
+
+def test_qk_convention_error_behaviour():
+    from streamflow_b200 import Aggregate
+    from streamflow_b200._lib import StreamCorrError
+    agg = Aggregate(args=_Args(), dim=128, heads=1, dim_head=128).cuda()
+    q = torch.zeros(1, 128, 8, 8, device="cuda")
+    with pytest.raises(StreamCorrError):
+        agg(q, torch.zeros(1, 128, 8, 9, device="cuda"), q)
+    with pytest.raises(StreamCorrError):
+        agg(q.cpu(), q.cpu(), q)
+    with pytest.raises(TypeError):
+        agg(q)
