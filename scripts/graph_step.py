@@ -16,8 +16,7 @@ with torch.no_grad():
 fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)
 
 def step():
-    blocks = [sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4) for i in range(3)]
-    group = sfb.CorrGroup(blocks)
+    group = sfb.CorrGroup.from_fmaps(fmaps, radius=4)
     handle = att(t["inps"])
     for it in range(12):
         feats = group([t["coords"][it, i] for i in range(3)])

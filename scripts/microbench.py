@@ -63,6 +63,7 @@ graph_time("group lookup (3 pairs)", lambda i: group(coords[i % 12]))
 graph_time("single-pair lookup", lambda i: blocks[0](coords[i % 12][0]))
 graph_time("aggregate (proj + agg)", lambda i: agg(handle, t["mfs"]))
 graph_time("corr build (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4), n=6)
+graph_time("corr group build (3 pairs)", lambda i: sfb.CorrGroup.from_fmaps(fmaps, radius=4), n=4)
 graph_time("corr build f16x2 (1 pair)", lambda i: sfb.CorrBlock(fmaps[:, i % 3], fmaps[:, i % 3 + 1], radius=4, precision="f16x2"), n=6)
 graph_time("attention (3 maps)", lambda i: att(t["inps"]), n=3)
 

@@ -152,6 +152,18 @@ class CorrBlock:
         self._level_ptrs = _lib.ptr_array([t.data_ptr() for t in self._levels])
         return self
 
+    @classmethod
+    def _from_tiled_levels(cls, levels, shape, precision, radius=4):
+        """Wrap level buffers (tiled layout, [B*N, th*tw*16] fp32 views) that a batched build already filled."""
+        self = cls.__new__(cls)
+        self.num_levels, self.radius, self.precision = _lib.NUM_LEVELS, radius, precision
+        self._shape = tuple(shape)
+        self._dims = _level_dims(shape[2], shape[3])
+        self._levels = list(levels)
+        self._pyramid_cache = None
+        self._level_ptrs = _lib.ptr_array([t.data_ptr() for t in self._levels])
+        return self
+
     @staticmethod
     def corr(fmap1, fmap2):
         """All-pairs correlation volume [B, h, w, 1, h, w] (core/corr.py:46-54)."""
@@ -179,6 +191,61 @@ class CorrGroup:
         self.blocks = blocks
         self.out_dtype = out_dtype
         self._level_ptrs = _lib.ptr_array([t.data_ptr() for b in blocks for t in b._levels])
+
+    @classmethod
+    def from_fmaps(cls, fmaps, radius=4, precision=None, out_dtype=torch.float32):
+        """Build the T-1 pyramids of a clip from its frame features ``fmaps [B, T, D, h, w]`` (any strides) and
+        return their group -- what ``core/models/streamflow.py:110`` does with T-1 ``CorrBlock(fmaps[:, i],
+        fmaps[:, i+1])`` calls.  For one clip (B = 1) the pairs are the batch of ONE build: frames 0..T-2 are packed
+        as queries, frames 1..T-1 as pooled targets, and a single persistent GEMM launch writes all pyramids.  For
+        B > 1 every pair index is one build batched over the clips.  ``group.blocks[i]`` are ordinary CorrBlocks."""
+        if radius != _lib.RADIUS:
+            raise StreamCorrError(f"CorrGroup is specialised for radius={_lib.RADIUS}; got {radius}")
+        if fmaps.dim() != 5 or fmaps.shape[1] < 2:
+            raise StreamCorrError(f"fmaps must be [B, T >= 2, D, h, w], got {tuple(fmaps.shape)}")
+        if not fmaps.is_cuda:
+            raise StreamCorrError("CorrGroup needs CUDA tensors (no CPU fallback)")
+        B, T, D, h, w = fmaps.shape
+        G = T - 1
+        if G > _lib.MAX_GROUPS:
+            raise StreamCorrError(f"CorrGroup takes 1..{_lib.MAX_GROUPS} pairs, got {G}")
+        prec = precision if precision is not None else _DEFAULT_PRECISION
+        if prec not in _lib.PRECISIONS:
+            raise StreamCorrError(f"unknown precision {prec!r}; choose from {sorted(_lib.PRECISIONS)}")
+        fm = fmaps.detach()
+        if fm.dtype != torch.float32:
+            fm = fm.float()
+        dev = fm.device
+        L = _lib.lib()
+        dims = _level_dims(h, w)
+        N = h * w
+        code = _lib.PRECISIONS[prec]
+        with _on_device(dev):
+            # block-major storage: pair g owns rows [g * B * N, (g + 1) * B * N) of every level
+            store = [torch.empty((G, B * N, th * tw * 16), dtype=torch.float32, device=dev)
+                     for (hl, wl, th, tw) in dims]
+            stream = _stream_ptr(dev)
+            if B == 1:
+                f1, f2 = fm[0, :-1], fm[0, 1:]
+                ws_bytes = L.sf_corr_workspace_bytes(G, D, h, w, code)
+                ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
+                rc = L.sf_corr_build(f1.data_ptr(), f2.data_ptr(), G, D, h, w, _lib.i64_array(f1.stride()),
+                                     _lib.i64_array(f2.stride()), _lib.ptr_array([t.data_ptr() for t in store]),
+                                     ws_ptr, ws_bytes, code, stream)
+                _lib.check(rc, "sf_corr_build")
+            else:
+                ws_bytes = L.sf_corr_workspace_bytes(B, D, h, w, code)
+                ws_buf, ws_ptr = _aligned_workspace(ws_bytes, dev)
+                for g in range(G):
+                    f1, f2 = fm[:, g], fm[:, g + 1]
+                    rc = L.sf_corr_build(f1.data_ptr(), f2.data_ptr(), B, D, h, w, _lib.i64_array(f1.stride()),
+                                         _lib.i64_array(f2.stride()),
+                                         _lib.ptr_array([t[g].data_ptr() for t in store]), ws_ptr, ws_bytes, code,
+                                         stream)
+                    _lib.check(rc, "sf_corr_build")
+            del ws_buf
+        blocks = [CorrBlock._from_tiled_levels([t[g] for t in store], (B, D, h, w), prec, radius) for g in range(G)]
+        return cls(blocks, out_dtype=out_dtype)
 
     def __call__(self, coords_list):
         blocks = self.blocks

@@ -4,6 +4,7 @@ streaming-window driver of configs[4] on one rank.  Tolerance: 1e-3 norm-wise (n
 import pytest
 import torch
 
+import streamflow_b200
 from oracle import torch_port as tp
 
 pytestmark = pytest.mark.gpu
@@ -175,3 +176,27 @@ def test_whole_step_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     want = step()[1]
     assert rel(out[1], want) < 1e-6
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_group_build_from_fmaps_matches_per_pair_blocks(B):
+    """CorrGroup.from_fmaps (one batched build of the T-1 pyramids) == T-1 CorrBlock builds,
+    on channels-last strided frame features as the model produces them."""
+    from streamflow_b200 import CorrBlock, CorrGroup
+    T, D, h, w = 4, 256, 24, 40
+    g = torch.Generator(device="cpu").manual_seed(5)
+    fm = torch.randn(B, T, h, w, D, generator=g).cuda().permute(0, 1, 4, 2, 3)       # channels-last views
+    coords = [(streamflow_b200.coords_grid(B, h, w, device="cuda") + 4 * torch.randn(B, 2, h, w, generator=g).cuda())
+              .contiguous() for _ in range(T - 1)]
+    group = CorrGroup.from_fmaps(fm, radius=4)
+    blocks = [CorrBlock(fm[:, i], fm[:, i + 1], radius=4) for i in range(T - 1)]
+    assert len(group.blocks) == T - 1
+    for gb, blk in zip(group.blocks, blocks):
+        for a, b in zip(gb.corr_pyramid, blk.corr_pyramid):
+            assert a.shape == b.shape
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+    out = group(coords)
+    ref = torch.stack([blk(c) for blk, c in zip(blocks, coords)], dim=1).reshape(B * (T - 1), 324, h, w)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(streamflow_b200.StreamCorrError):
+        CorrGroup.from_fmaps(fm[:, :1])
