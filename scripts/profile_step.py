@@ -20,8 +20,7 @@ with torch.no_grad():
     att.to_qk.weight.copy_(host["w_qk"].view(256, 128, 1, 1)); agg.to_v.weight.copy_(host["w_v"].view(128, 128, 1, 1)); agg.gamma.fill_(0.8)
 fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)
 for rep in range(2):
-    blocks = [sfb.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4) for i in range(3)]
-    group = sfb.CorrGroup(blocks)
+    group = sfb.CorrGroup.from_fmaps(fmaps, radius=4)
     handle = att(t["inps"])
     for it in range(iters):
         feats = group([t["coords"][it, i] for i in range(3)])
