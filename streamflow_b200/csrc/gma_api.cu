@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, v_off, rscale_off, eye_off, total;
+    int64_t q_off, k_off, rowmax_off, rowsum_fx_off, v_off, rscale_off, eye_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -18,6 +18,7 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.q_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
     ws.k_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
+    ws.rowsum_fx_off = off;  off += align_up(P * N * 8, 1024);
     ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
     ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
     ws.eye_off = off;     off += align_up(d * d * 4, 1024);
@@ -67,7 +68,7 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     if (int rc = launch_gma_proj(pk, s)) return rc;
 
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
-    SF_CUDA_CHECK(cudaMemsetAsync(rowsum, 0, P * N * 4, s));
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowsum_fx_off, 0, P * N * 8, s));
 
     CUtensorMap tm_q, tm_k, tm_e;
     const uint64_t kp = static_cast<uint64_t>(Kp);
@@ -92,12 +93,13 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     int chunks = (int)((4ll * di.sms + base_units - 1) / base_units);
     sp.chunks = std::max(1, std::min(chunks, sp.n_tiles));
     sp.rowmax_bits = reinterpret_cast<unsigned*>(wsb + ws.rowmax_off);
-    sp.rowsum = rowsum;
+    sp.rowsum_fx = reinterpret_cast<unsigned long long*>(wsb + ws.rowsum_fx_off);
     sp.E = static_cast<__half*>(E);
     sp.pass = 1;
     if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
     sp.pass = 2;
-    return launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s);
+    if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
+    return launch_gma_rowsum_finish(sp.rowsum_fx, rowsum, P * N, s);
 }
 
 }  // namespace

@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
             if (row_ok) {
                 if (p.pass == 1)
                     atomicMax(p.rowmax_bits + ridx, enc_ordered(run_max));
-                else
-                    atomicAdd(p.rowsum + ridx, run_sum);
+                else   // fp32 sum of fp16 values: always a multiple of 2^-24, so the conversion is exact
+                    atomicAdd(p.rowsum_fx + ridx, __float2ull_rn(run_sum * 16777216.0f));
             }
         }
         if (lane == 0) tma_store_wait_all<0>();
@@ -290,7 +290,21 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     }
 }
 
+__global__ void gma_rowsum_finish_kernel(const unsigned long long* fx, float* rowsum, long long n) {
+    pdl_launch();
+    pdl_wait();
+    const long long i = blockIdx.x * 256ll + threadIdx.x;
+    if (i < n) rowsum[i] = __ull2float_rn(fx[i]) * (1.0f / 16777216.0f);
+}
+
 }  // namespace
+
+int launch_gma_rowsum_finish(const unsigned long long* fx, float* rowsum, long long n, cudaStream_t s) {
+    SF_CUDA_CHECK(launch_kernel(gma_rowsum_finish_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s,
+                                fx, rowsum, n));
+    SF_CUDA_CHECK(cudaGetLastError());
+    return SF_OK;
+}
 
 int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
                      const CUtensorMap& tm_e, int num_sms, cudaStream_t s) {

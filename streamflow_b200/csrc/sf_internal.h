@@ -177,12 +177,14 @@ struct GmaStatsParams {
     int m_tiles, n_tiles;       // ceil(N/128), ceil(N/256)
     int chunks;                 // key-chunks per m-tile (work split)
     unsigned* rowmax_bits;      // [P, N] ordered-int encoded running max (pass 1 out / pass 2 in)
-    float* rowsum;              // [P, N] sum of stored E (pass 2 out, atomics)
+    unsigned long long* rowsum_fx;   // [P, N] sum of stored E in units of 2^-24 (pass 2 out): every fp16 value is a
+                                     // multiple of 2^-24, so integer atomics make the sum exact and order-independent
     __half* E;                  // [P, N, Npad]
     int pass;
 };
 int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
                      const CUtensorMap& tm_e, int num_sms, cudaStream_t s);
+int launch_gma_rowsum_finish(const unsigned long long* fx, float* rowsum, long long n, cudaStream_t s);
 
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
