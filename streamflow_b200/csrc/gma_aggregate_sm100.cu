@@ -420,7 +420,8 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num
     args.fbuf_pitch = 0;
     args.fbuf_off = args.rbuf_off = 0;
     const int fbuf_bytes = (kCh * (rows_cap * elt + 16) + rows_cap * 4 + 1023) / 1024 * 1024;
-    if (per_cta <= kMaxUnits && (static_cast<long long>(p.N) * elt) % 16 == 0 &&
+    // (one segment per CTA needs the per-map split, i.e. P <= grid: a linear split may straddle two maps)
+    if (p.P <= grid && per_cta <= kMaxUnits && (static_cast<long long>(p.N) * elt) % 16 == 0 &&
         (reinterpret_cast<uintptr_t>(p.fmap) & 15) == 0 && avail - fbuf_bytes >= 4 * args.e_stage_bytes) {
         args.fbuf_pitch = rows_cap * elt + 16;
         avail -= fbuf_bytes;

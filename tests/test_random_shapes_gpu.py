@@ -67,7 +67,11 @@ def test_low_precision_feature_maps_are_upcast(dtype):
     assert rel_err(blk.corr_pyramid[0].cpu().numpy(), pyr[0]) < 1e-3
 
 
-@pytest.mark.parametrize("P,h,w,seed", [(1, 9, 13, 1), (2, 16, 16, 2), (3, 11, 24, 3), (1, 40, 33, 4)])
+# The aggregate splits the query rows of all maps into 16-row units over the SMs; the extra cases pin its partition
+# edges: more maps than SMs with one unit each (160 x 16), a ragged last unit (N = 20), N not a multiple of 4
+# (scalar epilogue, N = 15), several CTAs per map with uneven runs (N = 156, 2600).
+@pytest.mark.parametrize("P,h,w,seed", [(1, 9, 13, 1), (2, 16, 16, 2), (3, 11, 24, 3), (1, 40, 33, 4),
+                                        (160, 4, 4, 5), (5, 4, 5, 6), (1, 3, 5, 7), (7, 12, 13, 8), (2, 50, 52, 9)])
 def test_gma_random_shapes(P, h, w, seed):
     from streamflow_b200 import Aggregate, Attention
 
