@@ -2,6 +2,7 @@
 // Each group of G/16 consecutive threads reads one random G-byte block as 16-byte loads; sums keep the loads alive.
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 template <int G>
@@ -41,8 +42,9 @@ void run(const float4* buf, size_t bytes, float* sink) {
            total / (best * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
 }
 
-int main() {
-    const size_t bytes = 800ull << 20;
+int main(int argc, char** argv) {
+    const size_t bytes = (argc > 1 ? static_cast<size_t>(atoi(argv[1])) : 800ull) << 20;
+    printf("buffer %zu MB\n", bytes >> 20);
     float4* buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 0, bytes);
     float* sink; cudaMalloc(&sink, 4);
     run<32>(buf, bytes, sink); run<64>(buf, bytes, sink); run<128>(buf, bytes, sink); run<256>(buf, bytes, sink);
