@@ -121,32 +121,33 @@ __global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant_
     };
     unsigned long long policy;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    // stage B2: all threads, thread = (query, tile column): issue the window's 16-byte chunks
+    // stage B2: all threads, thread = (query, row inside a tile): issue the window as 16-byte chunks
     auto issue_window = [&](int it, int buf) {
         if (it < items) {
             const Meta& m = meta[buf];
             const int lvl = m.lvl;
             const int th = p.th[lvl], tw = p.tw[lvl];
-            const int q = tid >> 2, j = tid & 3;
-            const float* base = m.img[q];
+            const int q = tid >> 2, rr = tid & 3;           // lane quad = the four 16-byte rows of ONE 64-byte tile:
+            const float* base = m.img[q];                   // every request carries two full sectors, fetched once
             const int x0 = m.x0[q], y0 = m.y0[q];
             const int ox = x0 & 3, oy = y0 & 3;             // window origin inside its first tile
-            const int txc = (x0 >> 2) + j, ty0 = y0 >> 2;
-            if (base != nullptr && 4 * j < ox + kRows) {    // tile column j overlaps window columns ox .. ox+9
-                const bool colok = (txc >= 0) && (txc < tw);
+            const int tx0 = x0 >> 2, ty0 = y0 >> 2;
+            if (base != nullptr) {
                 const unsigned rowmask = ((1u << kRows) - 1u) << oy;      // staged rows covered by the window
-                float* dst = win0 + buf * (kQ * kWinStride) + q * kWinStride + j * 4;
+                const int ncol = (ox + kRows + 3) >> 2;                   // tile columns overlapping window columns ox .. ox+9
+                float* dst = win0 + buf * (kQ * kWinStride) + q * kWinStride;
 #pragma unroll
-                for (int tr = 0; tr < 4; ++tr) {            // tile row: one 64-bit address per 64-byte tile
+                for (int tr = 0; tr < 4; ++tr) {            // tile row
+                    const int R = tr * 4 + rr;
+                    if (R >= kStageRows || !(rowmask & (1u << R))) continue;      // row outside the window
                     const int ty = ty0 + tr;
-                    const bool ok = colok && (ty >= 0) && (ty < th);
-                    const float* tile = ok ? base + ((ty * tw + txc) << 4) : base;
+                    const bool rowok = (ty >= 0) && (ty < th);
+                    const float* row = base + (rowok ? (ty * tw + tx0) * 16 + rr * 4 : 0);
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {        // row inside the tile: constant offsets from here on
-                        const int R = tr * 4 + rr;
-                        if (R >= kStageRows) continue;
-                        if (!(rowmask & (1u << R))) continue;      // outside the window (same 64 B block)
-                        cp_async16_zfill(dst + R * kRowFloats, tile + (ok ? rr * 4 : 0), ok, policy);
+                    for (int j = 0; j < 4; ++j) {           // tile column: constant 64-byte steps from here on
+                        if (j >= ncol) continue;
+                        const bool ok = rowok && (tx0 + j >= 0) && (tx0 + j < tw);
+                        cp_async16_zfill(dst + R * kRowFloats + j * 4, ok ? row + j * 16 : base, ok, policy);
                     }
                 }
             }
