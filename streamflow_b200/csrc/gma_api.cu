@@ -12,7 +12,7 @@ struct GmaWs {
 
 GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     GmaWs ws{};
-    ws.Kp = static_cast<int>(3 * d);            // room for hi/lo-split q, k (SF_PREC_F16X2); SF_PREC_F16 uses d
+    ws.Kp = static_cast<int>(2 * d);            // room for [hi | lo]-split q, k (SF_PREC_F16X2); SF_PREC_F16 uses d
     ws.Npad = align_up(N, 64);
     int64_t off = 0;
     ws.q_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);

@@ -4,7 +4,7 @@
 // 0.23 GFLOP per map: latency-, not throughput-critical, so this uses the warp-level mma.sync path
 // (m16n8k16, fp16 in / fp32 accumulate) with ldmatrix.trans for the n-contiguous X operand.  Results are
 // written in the layouts the tcgen05 kernels consume through TMA:
-//   token-major   [P, N, ld]    (q, k; optionally hi/lo split along K for fp32-faithful logits)
+//   token-major   [P, N, ld]    (q, k; optionally [hi | lo] split along K for fp32-faithful logits)
 //   channel-major [P, O, ld]    (v; ld = Npad, pad columns written as zero)
 #include <cuda_bf16.h>
 
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
     }
 
     // D fragment: acc[jt][0..1] -> (o = 16w + g, n = 8jt + 2t, +1); acc[jt][2..3] -> o + 8
-    const int parts = (p.token_major && p.split) ? 3 : 1;
+    // split output: [hi | lo] along K, lo = fp16(v - hi) unscaled (see gma_stats_kernel for the operand schedule)
+    const int parts = (p.token_major && p.split) ? 2 : 1;
     for (int part = 0; part < parts; ++part) {
         __syncthreads();   // Ds reuse (and Xs/Ws reads finished on the first pass)
 #pragma unroll
@@ -191,12 +192,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
                 const int n = jt * 8 + 2 * t + (e & 1);
                 const float v = acc[jt][e] * p.scale;
                 const __half hi = __float2half_rn(v);
-                __half val = hi;
-                if (part > 0) {
-                    const bool want_lo = (part == 1) == (p.is_b != 0);     // B: [hi | lo | hi'], A: [hi | hi' | lo]
-                    val = want_lo ? __float2half_rn((v - __half2float(hi)) * 2048.f)
-                                  : __float2half_rn(__half2float(hi) * (1.f / 2048.f));
-                }
+                const __half val = (part == 0) ? hi : __float2half_rn(v - __half2float(hi));
                 if (p.token_major)
                     Ds[n * 136 + o] = val;
                 else

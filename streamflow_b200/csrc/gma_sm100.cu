@@ -42,12 +42,14 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 // =====================================================================================================
 namespace st {
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 3;
-constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kMaxStages = 6, kMaxQBlocks = 4;          // K ring depth / resident Q k-blocks (hi and lo halves of d = 128)
+constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
 constexpr int kEpiWarps = 8;                            // two warps per TMEM lane quadrant, 128 columns each
-constexpr int kEpiBuf = 32 * 128;                       // 32 rows x 64 fp16
-constexpr int kEpiBytes = kEpiWarps * 2 * kEpiBuf;
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
+constexpr int kEpiBuf = 32 * 128;                       // 32 rows x 64 fp16, one staging buffer per warp
+constexpr int kEpiBytes = kEpiWarps * kEpiBuf;
+constexpr int kSmemBytes = 227 * 1024;
+constexpr int kBarBytes = 256;
+constexpr int kRing = (kSmemBytes - 1024 - kBarBytes - kEpiBytes) / 1024 * 1024;     // Q blocks + K stages
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 }  // namespace st
@@ -55,26 +57,42 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 struct GmaStatsArgs {
     CUtensorMap tm_q, tm_k, tm_e;
     GmaStatsParams p;
+    int stages;                     // K ring depth: whatever fits next to the resident Q blocks
 };
 
 __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
     using namespace st;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint8_t* epi_base = smem + kStages * kStageBytes;
+    // The 128-query Q tile of a work unit stays resident (one 16 KB block per 64 columns of K-depth, each with its own
+    // full/empty barrier so the next unit's blocks stream in behind the last key tile); only K tiles go through the ring.
+    uint8_t* q_base = smem;
+    const int kStages = args.stages;
+    uint8_t* epi_base = smem + kRing;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiBytes);
     uint64_t* full = bars;
-    uint64_t* empty = bars + kStages;
-    uint64_t* tfull = bars + 2 * kStages;
-    uint64_t* tempty = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* q_full = empty + kMaxStages;
+    uint64_t* q_empty = q_full + kMaxQBlocks;
+    uint64_t* tfull = q_empty + kMaxQBlocks;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const GmaStatsParams& p = args.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // pass 1 only needs an approximate row max (any m within a few units of the true max keeps exp() in range and
-    // cancels in E / rowsum): use the hi parts alone (first d columns); pass 2 uses the full hi/lo-split K
-    const int kblocks = ((p.pass == 1 && p.split) ? (p.Kp / 3 + BK - 1) / BK : (p.Kp + BK - 1) / BK);
+    // Operand schedule.  d-wide hi parts are `dblocks` 64-column blocks; with split operands (q = [hi | lo],
+    // k = [hi | lo], Kp = 2d) the logit is hi.hi + lo.hi + hi.lo: the K tile streams as hi_0, lo_0, hi_1, lo_1, ... and
+    // every K block is used while it sits in its stage -- hi_j against the resident Q_hi_j AND Q_lo_j, lo_j against
+    // Q_hi_j -- so each K byte is fetched once per tile (the earlier [hi | hi' | lo] x [hi | lo | hi'] packing
+    // streamed 3d columns for the same three products).  lo parts are stored unscaled: for |x| < 0.25 they are fp16
+    // subnormals with 2^-25 absolute error, far below the 2^-12 relative error of an unsplit operand.
+    // Pass 1 only needs an approximate row max (any m within a few units of the true max keeps exp() in range and
+    // cancels in E / rowsum): it uses the hi parts alone.
+    const bool split2 = (p.pass == 2) && p.split;
+    const int dblocks = (p.split ? p.Kp / 2 : p.Kp) / BK;
+    const int qblocks = split2 ? 2 * dblocks : dblocks;       // resident Q blocks; Q/K column of block b is b * BK
+    const int ksteps = qblocks;                               // K blocks streamed per key tile
+    uint8_t* stage_base = q_base + qblocks * kABytes;
     const int per_chunk = (p.n_tiles + p.chunks - 1) / p.chunks;
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const long long u_begin = units * blockIdx.x / gridDim.x;
@@ -84,9 +102,13 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
         tma_prefetch_desc(&args.tm_q);
         tma_prefetch_desc(&args.tm_k);
         tma_prefetch_desc(&args.tm_e);
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < kMaxQBlocks; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
@@ -115,47 +137,68 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, qphase = 0;
             for (long long u = u_begin; u < u_end; ++u) {
                 int pb, mt, nt0, nt1;
                 unit_coords(u, pb, mt, nt0, nt1);
+                if (nt0 >= nt1) continue;               // empty key chunk: no Q load, no phase flip
                 for (int nt = nt0; nt < nt1; ++nt)
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int t = 0; t < ksteps; ++t) {
+                        const int j = split2 ? (t >> 1) : t;
+                        const bool is_lo = split2 && (t & 1);
+                        if (nt == nt0 && !is_lo) {          // Q blocks first used by this step: free once the previous
+                            for (int b = j; b < qblocks; b += dblocks) {       // unit's last key tile has consumed them
+                                mbar_wait(&q_empty[b], qphase ^ 1);
+                                mbar_expect_tx(&q_full[b], kABytes);
+                                tma_load_3d(&args.tm_q, &q_full[b], q_base + b * kABytes, b * BK, mt * BM, pb);
+                            }
+                        }
                         mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = stage_base + stage * kStageBytes;
-                        mbar_expect_tx(&full[stage], kStageBytes);
-                        tma_load_3d(&args.tm_q, &full[stage], sa, kb * BK, mt * BM, pb);
-                        tma_load_3d(&args.tm_k, &full[stage], sa + kABytes, kb * BK, nt * BN, pb);
+                        mbar_expect_tx(&full[stage], kBBytes);
+                        tma_load_3d(&args.tm_k, &full[stage], stage_base + stage * kBBytes,
+                                    (is_lo ? dblocks + j : j) * BK, nt * BN, pb);
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
                         }
                     }
+                qphase ^= 1;
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
             int stage = 0, local = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, qphase = 0;
             for (long long u = u_begin; u < u_end; ++u) {
                 int pb, mt, nt0, nt1;
                 unit_coords(u, pb, mt, nt0, nt1);
+                if (nt0 >= nt1) continue;               // empty key chunk: no Q load, no phase flip
                 for (int nt = nt0; nt < nt1; ++nt, ++local) {
                     const int acc = local & 1;
                     mbar_wait(&tempty[acc], ((local >> 1) & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int t = 0; t < ksteps; ++t) {
+                        const int j = split2 ? (t >> 1) : t;
+                        const bool is_lo = split2 && (t & 1);
+                        const int n_a = (split2 && !is_lo) ? 2 : 1;        // K_hi_j meets Q_hi_j and Q_lo_j
+                        if (nt == nt0 && !is_lo)
+                            for (int b = j; b < qblocks; b += dblocks) mbar_wait(&q_full[b], qphase);
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-                        const uint64_t da = make_kmajor_sw128_desc(sa);
-                        const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+                        const uint64_t db = make_kmajor_sw128_desc(smem_u32(stage_base + stage * kBBytes));
+                        for (int a = 0; a < n_a; ++a) {
+                            const uint64_t da = make_kmajor_sw128_desc(smem_u32(q_base + (j + a * dblocks) * kABytes));
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | a | k) != 0);
+                        }
                         umma_commit(&empty[stage]);
+                        if (nt == nt1 - 1) {                // last use of a resident Q block in this unit
+                            if (!split2) umma_commit(&q_empty[j]);
+                            else umma_commit(&q_empty[is_lo ? j : dblocks + j]);
+                        }
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
@@ -163,13 +206,14 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                     }
                     umma_commit(&tfull[acc]);
                 }
+                qphase ^= 1;
             }
         }
     } else {
         const int e = warp - 2, quad = warp & 3, half = e >> 2;     // half: which 128 of the 256 key columns
-        uint8_t* bufs = epi_base + e * 2 * kEpiBuf;
+        uint8_t* buf = epi_base + e * kEpiBuf;
         const int kbk = p.Npad / 64;                                // 64-key blocks per row of E
-        int local = 0, buf_sel = 0;
+        int local = 0;
         for (long long u = u_begin; u < u_end; ++u) {
             int pb, mt, nt0, nt1;
             unit_coords(u, pb, mt, nt0, nt1);
@@ -213,8 +257,9 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                             }
                         }
                     } else {
-                        uint8_t* buf = bufs + buf_sel * kEpiBuf;
-                        if (lane == 0) tma_store_wait_read<1>();
+                        // one staging buffer per warp: the previous chunk's store has had the whole tcgen05.ld + exp
+                        // phase of this chunk to finish reading it
+                        if (lane == 0) tma_store_wait_read<0>();
                         __syncwarp();
                         __half2 h[32];
                         float sum0 = 0.f, sum1 = 0.f;
@@ -268,7 +313,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                             tma_store_3d(&args.tm_e, buf, 0, (mt * kbk + (col0 >> 6)) * BM + quad * 32, pb);
                             tma_store_commit();
                         }
-                        buf_sel ^= 1;
                     }
                 }
             }
@@ -313,6 +357,10 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     args.tm_k = tm_k;
     args.tm_e = tm_e;
     args.p = p;
+    const int d = p.split ? p.Kp / 2 : p.Kp;
+    SF_REQUIRE(d % st::BK == 0 && 2 * (d / st::BK) <= st::kMaxQBlocks, "gma_stats: head dimension %d not supported", d);
+    const int qblocks = (p.pass == 2 && p.split) ? 2 * (d / st::BK) : d / st::BK;
+    args.stages = std::min(st::kMaxStages, (st::kRing - qblocks * st::kABytes) / st::kBBytes);
     SF_CUDA_CHECK(cudaFuncSetAttribute(gma_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kSmemBytes));
     const long long units = static_cast<long long>(p.P) * p.m_tiles * p.chunks;
     const int grid = static_cast<int>(std::min<long long>(units, num_sms));

@@ -173,7 +173,7 @@ int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s);
 
 struct GmaStatsParams {
     int P, N, Npad, Kp;
-    int split;                  // Kp = 3d hi/lo-split operands (pass 1 then uses the first d columns only)
+    int split;                  // Kp = 2d, q = [hi | lo], k = [hi | lo] (pass 1 uses the hi halves only)
     int m_tiles, n_tiles;       // ceil(N/128), ceil(N/256)
     int chunks;                 // key-chunks per m-tile (work split)
     unsigned* rowmax_bits;      // [P, N] ordered-int encoded running max (pass 1 out / pass 2 in)
