@@ -76,7 +76,7 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
                             128, "Q"))
         return rc;
     if (int rc = make_tmap3(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.k_off, kp, N, P, kp * 2, N * kp * 2, 64,
-                            256, "K"))
+                            128, "K"))      // each CTA of a pair loads half of a 256-key tile
         return rc;
     // E is tile-major [P][m_tiles][Npad/64][128][64]: a 2-D view of 128-byte rows per map
     const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
@@ -89,8 +89,9 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = Kp; sp.split = split;
     sp.m_tiles = (int)((N + 127) / 128);
     sp.n_tiles = (int)((N + 255) / 256);
-    const int64_t base_units = P * sp.m_tiles;
-    int chunks = (int)((4ll * di.sms + base_units - 1) / base_units);
+    sp.pair_tiles = (sp.m_tiles + 1) / 2;
+    const int64_t base_units = P * sp.pair_tiles;
+    int chunks = (int)((4ll * (di.sms / 2) + base_units - 1) / base_units);
     sp.chunks = std::max(1, std::min(chunks, sp.n_tiles));
     sp.rowmax_bits = reinterpret_cast<unsigned*>(wsb + ws.rowmax_off);
     sp.rowsum_fx = reinterpret_cast<unsigned long long*>(wsb + ws.rowsum_fx_off);

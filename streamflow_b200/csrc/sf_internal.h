@@ -57,6 +57,26 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// Same for a kernel whose CTAs form clusters of `cluster_x` along x (grid.x must be a multiple of it).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         unsigned cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -175,6 +195,7 @@ struct GmaStatsParams {
     int P, N, Npad, Kp;
     int split;                  // Kp = 2d, q = [hi | lo], k = [hi | lo] (pass 1 uses the hi halves only)
     int m_tiles, n_tiles;       // ceil(N/128), ceil(N/256)
+    int pair_tiles;             // ceil(m_tiles / 2): a CTA pair owns two query tiles
     int chunks;                 // key-chunks per m-tile (work split)
     unsigned* rowmax_bits;      // [P, N] ordered-int encoded running max (pass 1 out / pass 2 in)
     unsigned long long* rowsum_fx;   // [P, N] sum of stored E in units of 2^-24 (pass 2 out): every fp16 value is a
