@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const CorrGemmParams& p = args.p;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so the compiler knows the role dispatch is warp-uniform (see gma_sm100.cu)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int kblocks = (p.Kp + BK - 1) / BK;
 
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp runs the loop; one elected lane issues
             constexpr uint32_t idesc = make_idesc_f16_f32(BM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -144,18 +145,21 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
                     const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
                     const uint64_t da = make_kmajor_sw128_desc(sa);
                     const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (kb == kblocks - 1) umma_commit(&tfull[acc]);
                     }
-                    umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);
             }
         }
     } else {

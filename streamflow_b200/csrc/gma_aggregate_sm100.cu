@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const GmaAggParams& p = args.p;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so the compiler knows the role dispatch is warp-uniform (see gma_sm100.cu)
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int KB = p.k_blocks;
     const int upm = args.units_per_map;
     const int e_stages = args.e_stages;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                       // ---- MMA issuer
+        {                                                      // ---- MMA issuer: warp-uniform loop, one elected lane issues
             int es = 0, vs = 0, local = 0;
             uint32_t ephase = 0, vphase = 0;
             long long u = u_begin;
@@ -263,10 +264,14 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(smem_u32(v_base + vs * kVBytes));
                     const uint64_t db = make_kmajor_sw128_desc(smem_u32(e_base + es * args.e_stage_bytes));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&e_empty[es]);
-                    umma_commit(&v_empty[vs]);
+                        for (int k = 0; k < BK / 16; ++k) umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit(&e_empty[es]);
+                        umma_commit(&v_empty[vs]);
+                        if (kb == KB - 1) umma_commit(&tfull[acc]);
+                    }
+                    __syncwarp();
                     if (++es == e_stages) {
                         es = 0;
                         ephase ^= 1;
@@ -276,7 +281,6 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
                         vphase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);
                 ++local;
             }
         }
