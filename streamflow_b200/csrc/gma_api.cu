@@ -61,11 +61,10 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     pq.scale = scale;
     pq.out = reinterpret_cast<__half*>(wsb + ws.q_off);
     pq.out_batch_stride = N * Kp; pq.ld = Kp; pq.token_major = 1; pq.split = split; pq.is_b = 0;
+    pq.x2 = xk; pq.w2 = w_k; pq.scale2 = 1.0f;                       // k rides in the same launch (blockIdx.z = 1)
+    pq.out2 = reinterpret_cast<__half*>(wsb + ws.k_off);
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "gma_attention: weight pointer must be 16-byte aligned");
     if (int rc = launch_gma_proj(pq, s)) return rc;
-    GmaProjParams pk = pq;
-    pk.x = xk; pk.w = w_k; pk.scale = 1.0f;
-    pk.out = reinterpret_cast<__half*>(wsb + ws.k_off); pk.is_b = 1;
-    if (int rc = launch_gma_proj(pk, s)) return rc;
 
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
     SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowsum_fx_off, 0, P * N * 8, s));

@@ -52,19 +52,26 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant__ GmaProjParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int C = p.C;
+    const bool second = blockIdx.z != 0;                             // q and k of one attention call share a launch
+    const void* px = second ? p.x2 : p.x;
+    const float* pw = second ? p.w2 : p.w;
+    const float pscale = second ? p.scale2 : p.scale;
+    __half* pout = second ? p.out2 : p.out;
     const int wpad = C + 8;
     __half* Xs = reinterpret_cast<__half*>(smem);                    // [C][kXPad]
     __half* Ws = Xs + C * kXPad;                                     // [128][C + 8]
-    __half* Ds = Ws + 128 * wpad;                                    // staging, 128 x 72 or 64 x 136
     // fp32-faithful projection (q, k): x = x_hi + x_lo, w = w_hi + w_lo in fp16, three MMA products
     const bool faithful = p.split != 0;
-    __half* Xl = Ds + 128 * kXPad;                                   // [C][kXPad]      (faithful only)
+    __half* Xl = Ws + 128 * wpad;                                    // [C][kXPad]      (faithful only)
     __half* Wl = Xl + C * kXPad;                                     // [128][C + 8]    (faithful only)
+    // output staging (128 x 72 or 64 x 136 halfs): reuses the X tile once the MMAs are done (two CTAs per SM then fit
+    // at C = 128); a narrower X tile is too small, so it gets its own space behind everything else
+    __half* Ds = (C >= 128) ? Xs : (faithful ? Wl + 128 * wpad : Xl);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * kTok;
     const int pb = blockIdx.y;
-    const T* X = reinterpret_cast<const T*>(p.x) + static_cast<long long>(pb) * C * p.N;
+    const T* X = reinterpret_cast<const T*>(px) + static_cast<long long>(pb) * C * p.N;
 
     pdl_launch();
     pdl_wait();
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
     }
     // X tile [C][64 tokens]: all global loads of a batch are issued before any conversion so they overlap
     const bool vec_ok = (sizeof(T) == 4) && ((p.N & 3) == 0) && (n0 + kTok <= p.N) &&
-                        ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+                        ((reinterpret_cast<uintptr_t>(px) & 15) == 0);
     for (int i0 = tid; i0 < C * (kTok / 4); i0 += 256 * 8) {
         float v[8][4];
 #pragma unroll
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * 256;
-            if (i < 128 * (C / 4)) wv[u] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+            if (i < 128 * (C / 4)) wv[u] = __ldg(reinterpret_cast<const float4*>(pw) + i);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
             for (int e = 0; e < 4; ++e) {
                 const int o = warp * 16 + g + (e >> 1) * 8;
                 const int n = jt * 8 + 2 * t + (e & 1);
-                const float v = acc[jt][e] * p.scale;
+                const float v = acc[jt][e] * pscale;
                 const __half hi = __float2half_rn(v);
                 const __half val = (part == 0) ? hi : __float2half_rn(v - __half2float(hi));
                 if (p.token_major)
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
             }
         __syncthreads();
         if (p.token_major) {      // rows = tokens, 128 outputs = 256 B per row
-            __half* out = p.out + static_cast<long long>(pb) * p.out_batch_stride + part * 128;
+            __half* out = pout + static_cast<long long>(pb) * p.out_batch_stride + part * 128;
             for (int i = tid; i < kTok * 16; i += 256) {
                 const int n = i >> 4, seg = i & 15;
                 if (n0 + n < p.N)
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
                         *reinterpret_cast<const int4*>(Ds + n * 136 + seg * 8);
             }
         } else {                  // rows = outputs, 64 tokens = 128 B per row; pad columns get the zeros
-            __half* out = p.out + static_cast<long long>(pb) * p.out_batch_stride;
+            __half* out = pout + static_cast<long long>(pb) * p.out_batch_stride;
             for (int i = tid; i < 128 * 8; i += 256) {
                 const int o = i >> 3, seg = i & 7;
                 if (n0 + seg * 8 < p.ld)
@@ -331,9 +338,9 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     SF_REQUIRE(p.ld % 8 == 0, "gma_proj: output pitch must be a multiple of 8");
     SF_REQUIRE((reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "gma_proj: weight pointer must be 16-byte aligned");
     const int base = (p.C * kXPad + 128 * (p.C + 8)) * 2;
-    const int smem = base + 128 * kXPad * 2 + (p.split ? base : 0);
+    const int smem = base + (p.split ? base : 0) + (p.C >= 128 ? 0 : 128 * kXPad * 2);
     const int cols = p.token_major ? p.N : p.ld;
-    dim3 grid((cols + kTok - 1) / kTok, p.P);
+    dim3 grid((cols + kTok - 1) / kTok, p.P, p.x2 != nullptr ? 2 : 1);
     auto launch = [&](auto kernel) -> int {
         SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         prof_before(SF_KERNEL_GMA_PROJ, s);

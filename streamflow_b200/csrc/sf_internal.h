@@ -182,6 +182,11 @@ struct GmaProjParams {
     int token_major;
     int split;            // token-major only: also write lo/hi split parts at column offsets O and 2*O
     int is_b;
+    // optional second projection in the same launch (blockIdx.z == 1): k next to q
+    const void* x2;
+    const float* w2;
+    float scale2;
+    __half* out2;
     // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the aggregate epilogue,
     // so that no later kernel has thousands of warps reading the single gamma word
     const float* rowsum;
