@@ -61,13 +61,13 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     pq.scale = scale;
     pq.out = reinterpret_cast<__half*>(wsb + ws.q_off);
     pq.out_batch_stride = N * Kp; pq.ld = Kp; pq.token_major = 1; pq.split = split; pq.is_b = 0;
+    pq.zero_u32 = reinterpret_cast<unsigned*>(wsb + ws.rowmax_off);          // row max / row sum accumulators of the
+    pq.zero_u64 = reinterpret_cast<unsigned long long*>(wsb + ws.rowsum_fx_off);   // stats passes start from zero
     pq.x2 = xk; pq.w2 = w_k; pq.scale2 = 1.0f;                       // k rides in the same launch (blockIdx.z = 1)
     pq.out2 = reinterpret_cast<__half*>(wsb + ws.k_off);
     SF_REQUIRE((reinterpret_cast<uintptr_t>(w_k) & 15) == 0, "gma_attention: weight pointer must be 16-byte aligned");
     if (int rc = launch_gma_proj(pq, s)) return rc;
 
-    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowmax_off, 0, P * N * 4, s));
-    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.rowsum_fx_off, 0, P * N * 8, s));
 
     CUtensorMap tm_q, tm_k, tm_e;
     const uint64_t kp = static_cast<uint64_t>(Kp);

@@ -79,6 +79,11 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
         const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
         p.rscale[r] = __ldg(p.gamma) / __ldg(p.rowsum + r);
     }
+    if (!second && tid < kTok && n0 + tid < p.N) {
+        const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
+        if (p.zero_u32 != nullptr) p.zero_u32[r] = 0u;
+        if (p.zero_u64 != nullptr) p.zero_u64[r] = 0ull;
+    }
     // X tile [C][64 tokens]: all global loads of a batch are issued before any conversion so they overlap
     const bool vec_ok = (sizeof(T) == 4) && ((p.N & 3) == 0) && (n0 + kTok <= p.N) &&
                         ((reinterpret_cast<uintptr_t>(px) & 15) == 0);

@@ -187,6 +187,9 @@ struct GmaProjParams {
     const float* w2;
     float scale2;
     __half* out2;
+    // optional: clear per-token accumulators of the following stats passes ([P, N] each) instead of two memsets
+    unsigned* zero_u32;
+    unsigned long long* zero_u64;
     // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the aggregate epilogue,
     // so that no later kernel has thousands of warps reading the single gamma word
     const float* rowsum;
