@@ -314,12 +314,13 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
         if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
                                 rows * kp * 2, 64, use_ra ? 128 : 256, "B"))
             return rc;
-        if (int rc = make_tmap3(&tm_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, levels[l], rows, N, B, rows * 4,
-                                N * rows * 4, 32, 32, "level"))
-            return rc;
+        if (use_ra)     // only the resident-A variant still stores through TMA
+            if (int rc = make_tmap3(&tm_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, levels[l], rows, N, B, rows * 4,
+                                    N * rows * 4, 32, 32, "level"))
+                return rc;
     }
     return use_ra ? launch_corr_gemm_ra(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s)
-                  : launch_corr_gemm(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s);
+                  : launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, s);
 }
 
 static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,

@@ -68,7 +68,9 @@ __device__ __forceinline__ Unit decode_unit(const CorrGemmRaArgs& a, long long u
 
 __global__ void __launch_bounds__(192, 1) corr_gemm_ra_kernel(const __grid_constant__ CorrGemmRaArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic (not through an integer) so the compiler keeps the shared address space: STS / LDS
+    // instead of generic ST / LD in the epilogue
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_base = smem;                                // [2 tiles][kblocks][128 x 64] fp16, 128B-swizzled
     uint8_t* b_base = smem + kABytes;                      // ring of [128 x 64] fp16
     uint8_t* epi_base = b_base + kStages * kBTileBytes;

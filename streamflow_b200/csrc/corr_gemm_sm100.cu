@@ -6,14 +6,14 @@
 // The four levels are extra N-tiles of the same GEMM (pooling is linear, see corr_pack.cu), so every pyramid
 // level is written exactly once, straight from the accumulator, and the 1/sqrt(D) scale is folded into the
 // epilogue.  The kernel is output-store bound (261 MB per Sintel pair vs 33 GFLOP): the design goal is that
-// TMA stores of tile i overlap the MMAs of tile i+1.
+// the stores of tile i overlap the MMAs of tile i+1.
 //
 // CTA = 192 threads, 1 CTA / SM, persistent over a contiguous range of (batch, m-tile, n-tile) tiles:
 //   warp 0      TMA producer: A (128 x 64) and B (256 x 64) fp16 k-blocks, 128B swizzle, 3-stage mbarrier ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16, kind::f16, fp32 accum),
 //               two 256-column accumulators in TMEM (double buffered against the epilogue)
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale -> swizzled smem -> TMA store (3-D map,
-//               clips ragged edges), four 4 KB staging buffers per warp = 64 KB of stores in flight per SM
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 64 columns -> scale -> swizzled smem -> transposed read-back ->
+//               st.global.cs: every store instruction writes four full 128-byte lines of the level image
 #include "sf_internal.h"
 #include "sm100_ptx.cuh"
 
@@ -23,7 +23,7 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 3;
-constexpr int kEpiBufs = 4;                           // staging buffers (TMA stores in flight) per epilogue warp
+constexpr int kEpiBufs = 4;                           // 4 KB staging buffers per epilogue warp (two pairs, ping-pong)
 constexpr int kABytes = BM * BK * 2;
 constexpr int kBBytes = BN * BK * 2;
 constexpr int kStageBytes = kABytes + kBBytes;
@@ -35,9 +35,9 @@ constexpr int kTmemCols = 512;
 struct CorrGemmArgs {
     CUtensorMap tm_a;
     CUtensorMap tm_b[SF_NUM_LEVELS];
-    CUtensorMap tm_out[SF_NUM_LEVELS];
     CorrGemmParams p;
-    int n_cols[SF_NUM_LEVELS];     // valid output columns per level (rows_l)
+    int n_cols[SF_NUM_LEVELS];     // valid output columns per level (rows_l) = row pitch of the level in floats
+    float* out[SF_NUM_LEVELS];     // level buffers [B * N, n_cols]
 };
 
 struct TileCoord {
@@ -65,7 +65,9 @@ __device__ __forceinline__ TileCoord decode_tile(const CorrGemmParams& p, long l
 
 __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant__ CorrGemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic (not through an integer) so the compiler keeps the shared address space: STS / LDS
+    // instead of generic ST / LD in the epilogue
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
     uint8_t* epi_base = smem + kStages * kStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiBytes);
@@ -88,7 +90,6 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
         tma_prefetch_desc(&args.tm_a);
         for (int l = 0; l < SF_NUM_LEVELS; ++l) {
             tma_prefetch_desc(&args.tm_b[l]);
-            tma_prefetch_desc(&args.tm_out[l]);
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full[i], 1);
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
     pdl_wait();        // everything above overlapped the previous kernel; its results are visible from here on
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // warp-uniform loop, one elected lane issues
             int stage = 0;
             uint32_t phase = 0;
             for (long long t = t_begin; t < t_end; ++t) {
@@ -117,9 +118,12 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * kStageBytes;
-                    mbar_expect_tx(&full[stage], kStageBytes);
-                    tma_load_3d(&args.tm_a, &full[stage], sa, kb * BK, c.mt * BM, c.b);
-                    tma_load_3d(&args.tm_b[c.level], &full[stage], sa + kABytes, kb * BK, c.ntl * BN, c.b);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[stage], kStageBytes);
+                        tma_load_3d(&args.tm_a, &full[stage], sa, kb * BK, c.mt * BM, c.b);
+                        tma_load_3d(&args.tm_b[c.level], &full[stage], sa + kABytes, kb * BK, c.ntl * BN, c.b);
+                    }
+                    __syncwarp();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -179,40 +183,58 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
             tc_fence_after();
             const int row0 = c.mt * BM + quad * 32;
             const int ncols = args.n_cols[c.level];
+            const long long pitch = ncols;
+            float* out_base = args.out[c.level] + static_cast<long long>(c.b) * p.N * pitch;
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + ch * 32, v);
+            for (int cp = 0; cp < BN / 64; ++cp) {      // 64 columns (two 32-column TMA boxes) per fence
+                uint32_t v0[32], v1[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cp * 64;
+                tmem_ld_32x32(taddr, v0);
+                tmem_ld_32x32(taddr + 32, v1);
                 tmem_ld_wait();
-                if (ch == BN / 32 - 1) {   // accumulator fully drained into registers: hand TMEM back
+                if (cp == BN / 64 - 1) {   // accumulator fully drained into registers: hand TMEM back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);
                 }
-                const int col0 = c.ntl * BN + ch * 32;
+                const int col0 = c.ntl * BN + cp * 64;
                 if (col0 >= ncols || row0 >= p.N) continue;          // warp-uniform
-                uint8_t* buf = bufs + buf_sel * kEpiBuf;
-                if (lane == 0) tma_store_wait_read<kEpiBufs - 1>();   // the store that last read `buf` is done
-                __syncwarp();
+                uint8_t* buf = bufs + buf_sel * (2 * kEpiBuf);
+                __syncwarp();               // the read-back of this buffer pair two iterations ago is complete
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 o;
-                    o.x = __uint_as_float(v[4 * j + 0]) * alpha;
-                    o.y = __uint_as_float(v[4 * j + 1]) * alpha;
-                    o.z = __uint_as_float(v[4 * j + 2]) * alpha;
-                    o.w = __uint_as_float(v[4 * j + 3]) * alpha;
+                    o.x = __uint_as_float(v0[4 * j + 0]) * alpha;
+                    o.y = __uint_as_float(v0[4 * j + 1]) * alpha;
+                    o.z = __uint_as_float(v0[4 * j + 2]) * alpha;
+                    o.w = __uint_as_float(v0[4 * j + 3]) * alpha;
                     *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    o.x = __uint_as_float(v1[4 * j + 0]) * alpha;
+                    o.y = __uint_as_float(v1[4 * j + 1]) * alpha;
+                    o.z = __uint_as_float(v1[4 * j + 2]) * alpha;
+                    o.w = __uint_as_float(v1[4 * j + 3]) * alpha;
+                    *reinterpret_cast<float4*>(buf + kEpiBuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
                 }
-                fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    tma_store_3d(&args.tm_out[c.level], buf, col0, row0, c.b);
-                    tma_store_commit();
+                // Transposed read-back: 8 lanes cover the 128 B of one row segment, so every store instruction writes
+                // four full 128-byte lines.  (TMA stores of the same 32-row x 128-byte boxes were the bottleneck of this
+                // kernel: ~250 clk of TMA-engine time per 4 KB box = 16 B/clk per SM = the 4.4 TB/s it was stuck at.)
+                const int sub = lane >> 3, chunk = lane & 7;
+                float* dst = out_base + static_cast<long long>(row0 + sub) * pitch + col0 + chunk * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + sub;
+                    const float4 a = *reinterpret_cast<const float4*>(buf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    const float4 bq = *reinterpret_cast<const float4*>(buf + kEpiBuf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    if (row0 + rr < p.N) {        // level images are multiples of 16 floats wide: clip per 16-byte chunk
+                        float* d = dst + static_cast<long long>(4 * i) * pitch;
+                        if (col0 + chunk * 4 < ncols) __stcs(reinterpret_cast<float4*>(d), a);
+                        if (col0 + 32 + chunk * 4 < ncols) __stcs(reinterpret_cast<float4*>(d + 32), bq);
+                    }
                 }
-                buf_sel = (buf_sel + 1) % kEpiBufs;
+                buf_sel ^= 1;
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -226,14 +248,14 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
 }  // namespace
 
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                     const CUtensorMap tm_out[SF_NUM_LEVELS], const int n_cols[SF_NUM_LEVELS], int num_sms,
+                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
                      cudaStream_t s) {
     CorrGemmArgs args;
     args.tm_a = tm_a;
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         args.tm_b[l] = tm_b[l];
-        args.tm_out[l] = tm_out[l];
         args.n_cols[l] = n_cols[l];
+        args.out[l] = levels[l];
     }
     args.p = p;
     static bool configured = false;

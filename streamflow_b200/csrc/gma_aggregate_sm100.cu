@@ -121,7 +121,9 @@ __device__ __forceinline__ void store_chunk(float* out, int n0, int N, bool vec,
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid_constant__ GmaAggArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic (not through an integer) so the compiler keeps the shared address space: STS / LDS
+    // instead of generic ST / LD in the epilogue
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* e_base = smem;
     uint8_t* v_base = smem + kRing - kVStages * kVBytes;     // [E ring | fmap tile + rscale (optional) | V ring | barriers]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing);

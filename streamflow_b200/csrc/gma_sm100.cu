@@ -73,7 +73,9 @@ struct GmaStatsArgs {
 __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid_constant__ GmaStatsArgs args) {
     using namespace st;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic (not through an integer) so the compiler keeps the shared address space: STS / LDS
+    // instead of generic ST / LD in the epilogue
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // The 128-query Q tile of a work unit stays resident (one 16 KB block per 64 columns of K-depth, each with its own
     // full/empty barrier so the next unit's blocks stream in behind the last key tile); only K tiles go through the ring.
     uint8_t* q_base = smem;

@@ -159,7 +159,7 @@ struct CorrGemmParams {
     float inv_sqrt_d;
 };
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                     const CUtensorMap tm_out[SF_NUM_LEVELS], const int n_cols[SF_NUM_LEVELS], int num_sms,
+                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
                      cudaStream_t s);
 
 // resident-A variant (corr_gemm_ra_sm100.cu): Kp <= 256; B tensor maps must use a 64 x 128 box
