@@ -69,7 +69,7 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     if (int rc = launch_gma_proj(pq, s)) return rc;
 
 
-    CUtensorMap tm_q, tm_k, tm_e;
+    CUtensorMap tm_q, tm_k;
     const uint64_t kp = static_cast<uint64_t>(Kp);
     if (int rc = make_tmap3(&tm_q, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.q_off, kp, N, P, kp * 2, N * kp * 2, 64,
                             128, "Q"))
@@ -77,13 +77,6 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     if (int rc = make_tmap3(&tm_k, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.k_off, kp, N, P, kp * 2, N * kp * 2, 64,
                             128, "K"))      // each CTA of a pair loads half of a 256-key tile
         return rc;
-    // E is tile-major [P][m_tiles][Npad/64][128][64]: a 2-D view of 128-byte rows per map
-    const uint64_t e_rows = static_cast<uint64_t>((N + 127) / 128) * (Npad / 64) * 128;
-    // no TMA swizzle on the store: HBM keeps the swizzled shared-memory image of every 16 KB block
-    if (int rc = make_tmap3(&tm_e, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, E, 64, e_rows, P, 128, e_rows * 128, 64, 32,
-                            "E(store)", /*swizzle128=*/false))
-        return rc;
-
     GmaStatsParams sp{};
     sp.P = (int)P; sp.N = (int)N; sp.Npad = (int)Npad; sp.Kp = Kp; sp.split = split;
     sp.m_tiles = (int)((N + 127) / 128);
@@ -96,9 +89,9 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     sp.rowsum_fx = reinterpret_cast<unsigned long long*>(wsb + ws.rowsum_fx_off);
     sp.E = static_cast<__half*>(E);
     sp.pass = 1;
-    if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
+    if (int rc = launch_gma_stats(sp, tm_q, tm_k, di.sms, s)) return rc;
     sp.pass = 2;
-    if (int rc = launch_gma_stats(sp, tm_q, tm_k, tm_e, di.sms, s)) return rc;
+    if (int rc = launch_gma_stats(sp, tm_q, tm_k, di.sms, s)) return rc;
     return launch_gma_rowsum_finish(sp.rowsum_fx, rowsum, P * N, s);
 }
 

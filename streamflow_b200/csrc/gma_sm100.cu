@@ -58,7 +58,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 }  // namespace st
 
 struct GmaStatsArgs {
-    CUtensorMap tm_q, tm_k, tm_e;
+    CUtensorMap tm_q, tm_k;
     GmaStatsParams p;
     int stages;                     // K ring depth: whatever fits next to the resident Q blocks
 };
@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.tm_q);
         tma_prefetch_desc(&args.tm_k);
-        tma_prefetch_desc(&args.tm_e);
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&full[i], 2);
             mbar_init(&empty[i], 1);
@@ -277,7 +276,7 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                 const bool full = col0 + 64 <= p.N;         // warp-uniform: no per-element key masking needed
                 if (p.pass == 2 && live) {
                     // one staging buffer per warp: the previous tile's store has had a whole tile period to be read
-                    if (lane == 0) tma_store_wait_read<0>();
+                    if (elect_one()) tma_store_wait_read<0>();
                     __syncwarp();
                 }
                 float sum0 = 0.f, sum1 = 0.f;
@@ -346,9 +345,15 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                     run_sum += sum0 + sum1;
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
-                        // E is tile-major: [P][m-tile][64-key block][128 rows][64 keys], 16 KB per tile
-                        tma_store_3d(&args.tm_e, buf, 0, (mt * kbk + (col0 >> 6)) * BM + quad * 32, pb);
+                    if (elect_one()) {
+                        // E is tile-major: [P][m-tile][64-key block][128 rows][64 keys]; the staging buffer already is
+                        // the swizzled image of its 32 rows, which are 4 KB contiguous in HBM: one bulk copy (a pair's
+                        // second CTA may hold a tile past the last one: nothing to store)
+                        if (mt < p.m_tiles) {
+                            __half* dst = p.E + (static_cast<long long>(pb) * p.m_tiles * kbk +
+                                                 static_cast<long long>(mt) * kbk + (col0 >> 6)) * (BM * 64) + quad * 32 * 64;
+                            bulk_store(dst, buf, kEpiBuf);
+                        }
                         tma_store_commit();
                     }
                 }
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(st::kThreads, 1) gma_stats_kernel(const __grid
                     atomicAdd(p.rowsum_fx + ridx, __float2ull_rn(run_sum * 16777216.0f));
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (elect_one()) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -387,12 +392,11 @@ int launch_gma_rowsum_finish(const unsigned long long* fx, float* rowsum, long l
     return SF_OK;
 }
 
-int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
-                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s) {
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k, int num_sms,
+                     cudaStream_t s) {
     GmaStatsArgs args;
     args.tm_q = tm_q;
     args.tm_k = tm_k;
-    args.tm_e = tm_e;
     args.p = p;
     const int d = p.split ? p.Kp / 2 : p.Kp;
     SF_REQUIRE(d == 2 * st::BK, "gma_stats: head dimension %d not supported (the issue loop is unrolled for d = 128)", d);

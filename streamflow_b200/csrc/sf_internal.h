@@ -211,8 +211,8 @@ struct GmaStatsParams {
     __half* E;                  // [P, N, Npad]
     int pass;
 };
-int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k,
-                     const CUtensorMap& tm_e, int num_sms, cudaStream_t s);
+int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUtensorMap& tm_k, int num_sms,
+                     cudaStream_t s);
 int launch_gma_rowsum_finish(const unsigned long long* fx, float* rowsum, long long n, cudaStream_t s);
 
 struct GmaAggParams {
