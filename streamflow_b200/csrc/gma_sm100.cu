@@ -6,8 +6,8 @@
 // exactly the matrix the reference's autocast path re-casts to fp16 every iteration (core/gma.py:95-97).
 // Every iteration is then one streaming GEMM  acc = E . V^T  bound by reading E from HBM:
 //
-//   gma_stats_kernel      S = Q K^T tiles (128 x 256, K = d or 3d for hi/lo-split operands) in TMEM;
-//                         pass 1 reduces the row max, pass 2 writes E with TMA stores and the row sums.
+//   gma_stats_kernel      S = Q K^T tiles (CTA pairs, 256 x 256; K = d, or [hi | lo] operands for three products) in TMEM;
+//                         pass 1 reduces the row max, pass 2 writes E (4 KB bulk stores) and the row sums.
 //   gma_aggregate_kernel  (gma_aggregate_sm100.cu) the per-iteration streaming GEMM with the fused epilogue.
 #include <type_traits>
 

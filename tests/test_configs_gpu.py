@@ -118,7 +118,7 @@ def test_kitti_gma_24_maps():
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_aggregate_low_precision_motion_features(dtype):
-    """Aggregate accepts fp16 / bf16 motion features (templated projection + finalize); result is fp32."""
+    """Aggregate accepts fp16 / bf16 motion features (templated projection and epilogue); result is fp32."""
     from streamflow_b200 import Aggregate, Attention
     torch.manual_seed(3)
     P, h, w = 2, 24, 40
