@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {                                       // ---- E producer
+        {                                                      // ---- E producer (warp-uniform loop, elected issue)
             int stage = 0;
             uint32_t phase = 0;
             long long u = u_begin;
@@ -213,15 +213,18 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&e_empty[stage], phase ^ 1);
                     uint8_t* dst = e_base + stage * args.e_stage_bytes;
-                    mbar_expect_tx(&e_full[stage], bytes);
                     const long long blk = static_cast<long long>(kb) * 128 * 64;
-                    bulk_load_hint(dst, src0 + blk, (cut1 - s.row0) * 128, &e_full[stage], kEvictFirst);
-                    if (cut1 < end)
-                        bulk_load_hint(dst + (cut1 - s.row0) * 128, src1 + blk, (cut2 - cut1) * 128, &e_full[stage],
-                                       kEvictFirst);
-                    if (cut2 < end)
-                        bulk_load_hint(dst + (cut2 - s.row0) * 128, src2 + blk, (end - cut2) * 128, &e_full[stage],
-                                       kEvictFirst);
+                    if (elect_one()) {
+                        mbar_expect_tx(&e_full[stage], bytes);
+                        bulk_load_hint(dst, src0 + blk, (cut1 - s.row0) * 128, &e_full[stage], kEvictFirst);
+                        if (cut1 < end)
+                            bulk_load_hint(dst + (cut1 - s.row0) * 128, src1 + blk, (cut2 - cut1) * 128, &e_full[stage],
+                                           kEvictFirst);
+                        if (cut2 < end)
+                            bulk_load_hint(dst + (cut2 - s.row0) * 128, src2 + blk, (end - cut2) * 128, &e_full[stage],
+                                           kEvictFirst);
+                    }
+                    __syncwarp();
                     if (++stage == e_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {                                       // ---- V producer
+        {                                                      // ---- V producer
             int stage = 0;
             uint32_t phase = 0;
             long long u = u_begin;
@@ -238,9 +241,12 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             while (next_seg(u, u_end, upm, s)) {
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&v_empty[stage], phase ^ 1);
-                    mbar_expect_tx(&v_full[stage], kVBytes);
-                    tma_load_3d_hint(&args.tm_v, &v_full[stage], v_base + stage * kVBytes, kb * BK, 0, s.pb,
-                                     kEvictLast);
+                    if (elect_one()) {
+                        mbar_expect_tx(&v_full[stage], kVBytes);
+                        tma_load_3d_hint(&args.tm_v, &v_full[stage], v_base + stage * kVBytes, kb * BK, 0, s.pb,
+                                         kEvictLast);
+                    }
+                    __syncwarp();
                     if (++stage == kVStages) {
                         stage = 0;
                         phase ^= 1;
