@@ -70,6 +70,21 @@ def test_no_device_means_loud_failure(L):
         Attention(args=A(), dim=128, heads=1, dim_head=128)(torch.zeros(1, 128, 8, 8))
     with pytest.raises(StreamCorrError):
         Aggregate(args=A(), dim=128, heads=1, dim_head=128)(None, torch.zeros(1, 128, 8, 8))
+    # the batched build, the (q, k, fmap) convention and the raw (q, k) entry point refuse CPU tensors the same way
+    from streamflow_b200 import CorrGroup
+    with pytest.raises(StreamCorrError):
+        CorrGroup.from_fmaps(torch.zeros(1, 4, 8, 16, 16))
+    with pytest.raises(StreamCorrError):
+        CorrGroup.from_fmaps(torch.zeros(1, 1, 8, 16, 16))            # fewer than two frames
+    agg = Aggregate(args=A(), dim=128, heads=1, dim_head=128)
+    q = torch.zeros(1, 128, 8, 8)
+    with pytest.raises(StreamCorrError):
+        agg(q, q, q)
+    with pytest.raises(TypeError):
+        agg(q)
+    qk = Attention(args=A(), dim=128, heads=1, dim_head=128, return_qk=True)(q)      # the projection itself is torch
+    assert len(qk) == 2 and qk[0].shape == (1, 128, 8, 8)
+    assert L.sf_gma_attention_qk(1024, 1024, 0, 1, 64, 128, 0.1, 1, 1024, 1024, 1024, 1 << 30, None) != 0
     # the raw entry points also fail (return code, not a crash)
     import ctypes
     lv = (ctypes.c_void_p * 4)(1024, 1024, 1024, 1024)
