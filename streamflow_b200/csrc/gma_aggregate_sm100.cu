@@ -15,9 +15,11 @@
 //     contiguous in HBM and lands with ONE non-tensor bulk copy (cp.async.bulk); a row range touches at most 3
 //     blocks.  (Fetching the same rows as power-of-two TMA boxes cost 4-9 TMA instructions per key block and ran
 //     at half the speed: per-instruction TMA cost, not bytes, was the limit.)
-// Memory-level parallelism is the whole game: the kernel is latency-bound until ~160 KB of E per SM are in flight
-// (measured: 108 KB in flight -> 4.4 TB/s, 160 KB -> 6 TB/s).  The E ring takes every byte of shared memory that
-// the 3-stage V ring (16 KB per key block, L2 resident, evict_last) leaves: 9 stages x 18 KB at Sintel size.
+// Ring sizing: bulk copies of >= 16 KB saturate HBM with as few as 3 stages (scripts/probes/stream_probe.cu), so the
+// E ring simply takes the shared memory that the 3-stage V ring (16 KB per key block, L2 resident, evict_last) and the
+// prefetched fmap tile of the staged epilogue leave: 5 stages x 18 KB at Sintel size.  What does matter is the work
+// split: a CTA that straddles two maps runs the key loop twice (twice the V traffic and iterations for the same E
+// bytes) and was the tail of the whole kernel (98 us) until the split became per-map.
 //
 // warps: 0 = E producer (bulk copies), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-10 = epilogue.
 #include <cuda_bf16.h>
