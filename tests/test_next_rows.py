@@ -76,3 +76,40 @@ def test_input_padder_sintel_and_kitti():
     assert padk._pad == [3, 3, 0, 1] and padk.pad(k)[0].shape[-2:] == (376, 1248)
     assert padk.unpad(padk.pad(k)[0]).shape == k.shape
     assert flowio.InputPadder((376, 1248))._pad == [0, 0, 0, 0]
+
+
+def test_kitti_flow_png_layout_and_reference_semantics(tmp_path):
+    """KITTI 16-bit flow PNG (core/utils/frame_utils.py:118-123, 137-141): R = 64u + 2^15, G = 64v + 2^15, B = valid;
+    byte layout checked directly, pixel equality with the reference's cv2 writer / reader when cv2 is present."""
+    import struct
+    import zlib
+    import numpy as np
+    from streamflow_b200.flowio import read_flow_kitti, write_flow_kitti
+    rs = np.random.RandomState(3)
+    uv = (rs.standard_normal((19, 23, 2)) * 30).astype(np.float32)
+    valid = rs.uniform(size=(19, 23)) > 0.25
+    p = str(tmp_path / "flow.png")
+    write_flow_kitti(p, torch.from_numpy(uv).permute(2, 0, 1), valid)          # [2, H, W] tensor accepted
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n" and raw[12:16] == b"IHDR"
+    w, h, depth, ctype = struct.unpack(">IIBB", raw[16:26])
+    assert (w, h, depth, ctype) == (23, 19, 16, 2)
+    n = struct.unpack(">I", raw[33:37])[0]
+    assert raw[37:41] == b"IDAT"
+    lines = np.frombuffer(zlib.decompress(raw[41:41 + n]), np.uint8).reshape(19, 1 + 23 * 6)
+    assert (lines[:, 0] == 0).all()
+    px = lines[:, 1:].copy().view(">u2").reshape(19, 23, 3)
+    want = (64.0 * uv + 2 ** 15).astype(np.uint16)                              # the reference's quantisation
+    assert np.array_equal(px[..., :2], want) and np.array_equal(px[..., 2] != 0, valid)
+    flow, v = read_flow_kitti(p)
+    assert flow.dtype == np.float32 and np.abs(flow - uv).max() <= 1 / 64 and np.array_equal(v != 0, valid)
+    with pytest.raises(ValueError):
+        write_flow_kitti(p, np.full((4, 4, 2), 600.0, np.float32))              # outside the 16-bit range
+    cv2 = pytest.importorskip("cv2")
+    ref = cv2.imread(p, cv2.IMREAD_ANYDEPTH | cv2.IMREAD_COLOR)[:, :, ::-1].astype(np.float32)   # readFlowKITTI
+    assert np.array_equal((ref[:, :, :2] - 2 ** 15) / 64.0, flow) and np.array_equal(ref[:, :, 2], v)
+    p2 = str(tmp_path / "ref.png")                                              # writeFlowKITTI -> our reader
+    arr = np.concatenate([64.0 * uv + 2 ** 15, np.ones((19, 23, 1))], axis=-1).astype(np.uint16)
+    cv2.imwrite(p2, arr[..., ::-1])
+    flow2, v2 = read_flow_kitti(p2)                                             # cv2 uses PNG filters: exercises them
+    assert np.array_equal(flow2, flow) and (v2 == 1).all()
