@@ -90,6 +90,17 @@ def lib() -> ctypes.CDLL:
     return L
 
 
+def require_no_grad(what: str, *tensors) -> None:
+    """The kernels are inference-only (no backward exists): refuse to run where autograd would expect a graph,
+    instead of silently returning tensors without grad_fn (the reference modules are differentiable and trained
+    through, train_mf.py:238-257)."""
+    import torch
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise StreamCorrError(
+            f"{what}: an input or parameter requires grad, but the B200 operators are inference-only (no backward "
+            "kernels). Run under torch.no_grad() / torch.inference_mode(), or use the reference operators to train.")
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().sf_last_error().decode("utf-8", "replace")

@@ -73,6 +73,7 @@ class CorrBlock:
                                   f"and {tuple(fmap2.shape)}")
         if not fmap1.is_cuda or fmap1.device != fmap2.device:
             raise StreamCorrError("CorrBlock needs CUDA tensors on one device (no CPU fallback)")
+        _lib.require_no_grad("CorrBlock", fmap1, fmap2)
         prec = precision if precision is not None else _DEFAULT_PRECISION
         if prec not in _lib.PRECISIONS:
             raise StreamCorrError(f"unknown precision {prec!r}; choose from {sorted(_lib.PRECISIONS)}")
@@ -80,8 +81,8 @@ class CorrBlock:
         self.radius = radius
         self.precision = prec
         # the model hands over fp32 maps (streamflow.py:107 `.float()`); other float dtypes are upcast
-        f1 = fmap1 if fmap1.dtype == torch.float32 else fmap1.float()
-        f2 = fmap2 if fmap2.dtype == torch.float32 else fmap2.float()
+        f1 = fmap1.detach() if fmap1.dtype == torch.float32 else fmap1.detach().float()
+        f2 = fmap2.detach() if fmap2.dtype == torch.float32 else fmap2.detach().float()
         B, D, h, w = f1.shape
         self._shape = (B, D, h, w)
         dev = f1.device
@@ -118,6 +119,7 @@ class CorrBlock:
         dev = self._levels[0].device
         if coords.device != dev:
             raise StreamCorrError("coords live on a different device than the correlation pyramid")
+        _lib.require_no_grad("CorrBlock.__call__", coords)
         c = coords.detach()
         if c.dtype != torch.float32 or not c.is_contiguous():
             c = c.float().contiguous()
@@ -212,6 +214,7 @@ class CorrGroup:
         prec = precision if precision is not None else _DEFAULT_PRECISION
         if prec not in _lib.PRECISIONS:
             raise StreamCorrError(f"unknown precision {prec!r}; choose from {sorted(_lib.PRECISIONS)}")
+        _lib.require_no_grad("CorrGroup.from_fmaps", fmaps)
         fm = fmaps.detach()
         if fm.dtype != torch.float32:
             fm = fm.float()
@@ -258,6 +261,7 @@ class CorrGroup:
         for c in coords_list:
             if tuple(c.shape) != (B, 2, h, w):
                 raise StreamCorrError(f"coords must be [{B}, 2, {h}, {w}], got {tuple(c.shape)}")
+            _lib.require_no_grad("CorrGroup.__call__", c)
             c = c.detach()
             cs.append(c if (c.dtype == torch.float32 and c.is_contiguous()) else c.float().contiguous())
         L = _lib.lib()

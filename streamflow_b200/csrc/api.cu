@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "sf_internal.h"
 
@@ -74,12 +77,12 @@ int query_device(DeviceInfo* out) {
         cache.dev = dev;
         cache.sms = sms;
         cache.ok = (major == 10) ? 1 : 0;
-        // The lookup gathers 48-64 B row segments: fetching 32 B sectors instead of the default 64 B pairs on an
-        // L2 miss cuts its DRAM over-fetch (measured with ncu, profiles/).  STREAMCORR_L2_FETCH=0 leaves the
-        // device limit untouched, 64 / 128 select the other granularities.
+        // STREAMCORR_L2_FETCH=32|64|128 (opt-in, measurement only) changes cudaLimitMaxL2FetchGranularity for the
+        // WHOLE device/process -- it also applies to every other kernel (cuDNN / cuBLAS of the update block), so the
+        // library never touches it unless asked; it made no measurable difference to the lookup.
         if (cache.ok == 1) {
             const char* env = getenv("STREAMCORR_L2_FETCH");
-            const int gran = env ? atoi(env) : 32;
+            const int gran = env ? atoi(env) : 0;
             if (gran == 32 || gran == 64 || gran == 128) {
                 if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(gran)) != cudaSuccess)
                     cudaGetLastError();
@@ -91,6 +94,23 @@ int query_device(DeviceInfo* out) {
         return SF_ERR_NODEVICE;
     }
     *out = cache;
+    return SF_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember what each device already has so a
+// launch costs no driver call, and a second device in the same process (nn.DataParallel, evaluate_mf.py:1207) gets
+// its own opt-in instead of an invalid-value launch failure.
+int ensure_dynamic_smem(const void* func, int bytes) {
+    int dev = 0;
+    SF_CUDA_CHECK(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> configured;
+    std::lock_guard<std::mutex> lock(mu);
+    int& cur = configured[std::make_pair(func, dev)];
+    if (bytes > cur) {
+        SF_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        cur = bytes;
+    }
     return SF_OK;
 }
 
@@ -118,6 +138,24 @@ EncodeTiledFn get_encode_fn() {
 
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, bool swizzle128) {
+    // A tensor map is a pure function of its arguments (the driver call costs ~1-2 us, and a step re-encodes the
+    // same ~10 maps for every clip of a stream): small per-thread direct-mapped cache keyed by all of them.
+    struct Entry {
+        uint64_t key[9];
+        bool valid = false;
+        CUtensorMap map;
+    };
+    constexpr int kSlots = 64;
+    static thread_local Entry cache[kSlots];
+    const uint64_t key[9] = {static_cast<uint64_t>(dt), reinterpret_cast<uint64_t>(base), d0, d1, d2, stride1, stride2,
+                             (static_cast<uint64_t>(b0) << 32) | b1, static_cast<uint64_t>(swizzle128)};
+    uint64_t hsh = 1469598103934665603ull;
+    for (uint64_t k : key) hsh = (hsh ^ k) * 1099511628211ull;
+    Entry& e = cache[(hsh >> 17) % kSlots];
+    if (e.valid && memcmp(e.key, key, sizeof(key)) == 0) {
+        *m = e.map;
+        return SF_OK;
+    }
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -137,6 +175,9 @@ int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_
                   (unsigned long long)stride1, (unsigned long long)stride2);
         return SF_ERR_CUDA;
     }
+    memcpy(e.key, key, sizeof(key));
+    e.map = *m;
+    e.valid = true;
     return SF_OK;
 }
 
@@ -296,15 +337,7 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     gp.amax_bits = amax;
     gp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
 
-    // STREAMCORR_GEMM=ra selects the resident-A kernel (Kp <= 256): 35 % less L2 traffic but measured 4 us slower
-    // than the streaming kernel (82 vs 78 us per build) -- the GEMM is bound by the scattered 128-byte DRAM writes
-    // of the volume, not by operand re-reads -- so the streaming kernel stays the default
-    static const bool want_ra = [] {
-        const char* e = getenv("STREAMCORR_GEMM");
-        return e && strcmp(e, "ra") == 0;
-    }();
-    const bool use_ra = want_ra && corr_gemm_ra_supported(ws.Kp);
-    CUtensorMap tm_a, tm_b[SF_NUM_LEVELS], tm_out[SF_NUM_LEVELS];
+    CUtensorMap tm_a, tm_b[SF_NUM_LEVELS];
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
     if (int rc = make_tmap3(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.a_off, kp, N, B, kp * 2, N * kp * 2, 64,
                             128, "A"))
@@ -312,15 +345,10 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         const uint64_t rows = static_cast<uint64_t>(g.img[l]);
         if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
-                                rows * kp * 2, 64, use_ra ? 128 : 256, "B"))
+                                rows * kp * 2, 64, 256, "B"))
             return rc;
-        if (use_ra)     // only the resident-A variant still stores through TMA
-            if (int rc = make_tmap3(&tm_out[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, levels[l], rows, N, B, rows * 4,
-                                    N * rows * 4, 32, 32, "level"))
-                return rc;
     }
-    return use_ra ? launch_corr_gemm_ra(gp, tm_a, tm_b, tm_out, n_cols, di.sms, s)
-                  : launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, s);
+    return launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, s);
 }
 
 static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,

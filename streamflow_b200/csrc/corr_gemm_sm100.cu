@@ -258,11 +258,7 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
         args.out[l] = levels[l];
     }
     args.p = p;
-    static bool configured = false;
-    if (!configured) {
-        SF_CUDA_CHECK(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(corr_gemm_kernel), kSmemBytes)) return rc;
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
     const int grid = static_cast<int>(std::min<long long>(total, num_sms));
     prof_before(SF_KERNEL_CORR_GEMM, s);

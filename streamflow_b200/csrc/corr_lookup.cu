@@ -248,7 +248,7 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
     // 4 CTAs of 55 KB per SM, persistent over the work items
     const int grid = static_cast<int>(std::min<long long>(p.items, 4ll * num_sms));
     auto launch = [&](auto kernel) -> int {
-        SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLookupSmem));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kLookupSmem)) return rc;
         prof_before(SF_KERNEL_LOOKUP, s);
         SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(128), static_cast<size_t>(kLookupSmem), s, p));
         prof_after(SF_KERNEL_LOOKUP, s);

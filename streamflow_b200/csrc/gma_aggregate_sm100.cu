@@ -406,8 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
 
 template <typename T>
 int launch_typed(const GmaAggArgs& args, int grid, cudaStream_t s) {
-    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_aggregate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSmemBytes));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gma_aggregate_kernel<T>), kSmemBytes)) return rc;
     prof_before(SF_KERNEL_GMA_AGGREGATE, s);
     SF_CUDA_CHECK(launch_kernel(gma_aggregate_kernel<T>, dim3(grid), dim3(kThreads), kSmemBytes, s, args));
     prof_after(SF_KERNEL_GMA_AGGREGATE, s);

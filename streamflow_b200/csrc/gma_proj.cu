@@ -347,7 +347,7 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     const int cols = p.token_major ? p.N : p.ld;
     dim3 grid((cols + kTok - 1) / kTok, p.P, p.x2 != nullptr ? 2 : 1);
     auto launch = [&](auto kernel) -> int {
-        SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
         prof_before(SF_KERNEL_GMA_PROJ, s);
         SF_CUDA_CHECK(launch_kernel(kernel, grid, dim3(256), static_cast<size_t>(smem), s, p));
         prof_after(SF_KERNEL_GMA_PROJ, s);
@@ -369,7 +369,7 @@ int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s) {
     const int smem = (2 * 128 * kXPadV + 128 * (128 + 8)) * 2;
     dim3 grid((p.ld + kTokV - 1) / kTokV, p.P);
     auto launch = [&](auto kernel) -> int {
-        SF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
         prof_before(SF_KERNEL_GMA_PROJ, s);
         SF_CUDA_CHECK(launch_kernel(kernel, grid, dim3(256), static_cast<size_t>(smem), s, p));
         prof_after(SF_KERNEL_GMA_PROJ, s);

@@ -402,7 +402,7 @@ int launch_gma_stats(const GmaStatsParams& p, const CUtensorMap& tm_q, const CUt
     SF_REQUIRE(d == 2 * st::BK, "gma_stats: head dimension %d not supported (the issue loop is unrolled for d = 128)", d);
     const int qblocks = (p.pass == 2 && p.split) ? 2 * (d / st::BK) : d / st::BK;
     args.stages = std::min(st::kMaxStages, (st::kRing - qblocks * st::kABytes) / st::kBBytes);
-    SF_CUDA_CHECK(cudaFuncSetAttribute(gma_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, st::kSmemBytes));
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gma_stats_kernel), st::kSmemBytes)) return rc;
     const long long units = static_cast<long long>(p.P) * p.pair_tiles * p.chunks;
     const int grid = 2 * static_cast<int>(std::min<long long>(units, num_sms / 2));       // CTA pairs
     prof_before(SF_KERNEL_GMA_STATS, s);

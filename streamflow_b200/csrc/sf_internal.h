@@ -98,6 +98,8 @@ struct DeviceInfo {
     int sms = 0;
     int dev = -1;
 };
+// Opt the kernel `func` in to `bytes` of dynamic shared memory on the CURRENT device (remembered per device).
+int ensure_dynamic_smem(const void* func, int bytes);
 // SF_OK and fills `out` when the current device is sm_100; SF_ERR_NODEVICE (with message) otherwise.
 int query_device(DeviceInfo* out);
 // rank-3 tiled TMA map, 128B swizzle: dims / box innermost first; strides (bytes) of dims 1 and 2; box[2] = 1.
@@ -161,12 +163,6 @@ struct CorrGemmParams {
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
                      const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
                      cudaStream_t s);
-
-// resident-A variant (corr_gemm_ra_sm100.cu): Kp <= 256; B tensor maps must use a 64 x 128 box
-bool corr_gemm_ra_supported(int Kp);
-int launch_corr_gemm_ra(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                        const CUtensorMap tm_out[SF_NUM_LEVELS], const int n_cols[SF_NUM_LEVELS], int num_sms,
-                        cudaStream_t s);
 
 // ----------------------------------------------------------------------- GMA (gma_sm100.cu)
 struct GmaProjParams {

@@ -66,7 +66,7 @@ def gather_flows(local: torch.Tensor, counts: Sequence[int], group=None) -> torc
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if len(counts) != world or local.shape[0] != counts[rank]:
         raise ValueError("counts must list every rank's number of flows")
-    cap = max(counts)
+    cap = max(counts)       # `counts` is identical on every rank, so all ranks take the same branch
     if cap == 0:
         return local
     padded = local.new_zeros((cap,) + tuple(local.shape[1:]))
@@ -106,18 +106,15 @@ def run_clips(clips: Sequence, flow_fn: Callable, group=None) -> torch.Tensor:
     """Independent clips sharded over ranks; ``flow_fn(clip) -> Tensor[T-1, 2, H, W]``; gathered in clip order."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    # validated BEFORE any collective, from arguments every rank shares, so all ranks raise identically (a rank
+    # that bailed out after its peers entered a collective would leave them hanging)
+    if len(clips) < world:
+        raise ValueError(f"run_clips: {len(clips)} clips for {world} ranks (every rank needs at least one clip)")
     parts = partition(len(clips), world)
     outs = [flow_fn(clips[i]) for i in parts[rank]]
-    per = None
-    if outs:
-        per = outs[0].shape[0]
-        local = torch.cat(outs, 0)
-    if world > 1:
-        # every rank needs the per-clip flow count to size the gather
-        t = torch.tensor([per if per is not None else 0], device=outs[0].device if outs else "cpu")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        per = int(t.item())
-    if not outs:
-        raise ValueError("run_clips: a rank received no clips (use at least `world` clips)")
+    per = outs[0].shape[0]
+    if any(o.shape[0] != per for o in outs):
+        raise ValueError("run_clips: flow_fn must return the same number of flows for every clip")
+    local = torch.cat(outs, 0)
     counts = [len(parts[r]) * per for r in range(world)]
     return gather_flows(local, counts, group)

@@ -18,7 +18,9 @@ attention with ``flash_attn_func`` every refinement iteration, this module build
 and reuses it for as long as the same, unmodified tensors come back.
 
 The kernels are specialised for the shipped configuration heads=1, dim=dim_head=128; anything else raises
-(there is no eager fallback).
+(there is no eager fallback).  Both modules are INFERENCE-ONLY: there are no backward kernels, so a call made with
+autograd enabled on inputs or parameters that require grad raises ``StreamCorrError`` instead of silently returning
+tensors without ``grad_fn`` (the parameters exist so that reference checkpoints load unchanged).
 """
 from __future__ import annotations
 
@@ -68,18 +70,26 @@ class AttentionHandle:
         return e.reshape(P, mt * 128)[:, :N]
 
 
+def _version_of(t):
+    """In-place modification counter, or None for inference tensors (they do not track versions)."""
+    return None if t.is_inference() else t._version
+
+
 def _weight_2d(module, attr, param, rows, cols, dtype=torch.float32):
     """contiguous [rows, cols] copy/view of a conv weight in `dtype`, cached until the parameter is modified in
-    place or replaced (keeps the reshape / conversion off every call)."""
-    key = (param.data_ptr(), param._version, param.dtype, param.device)
+    place or replaced (keeps the reshape / conversion off every call).  The cache holds the parameter tensor itself
+    and compares identity, so a new tensor that happens to reuse the storage address cannot hit; inference tensors
+    (no version counter) are never cached."""
+    ver = _version_of(param)
     cached = getattr(module, attr, None)
-    if cached is None or cached[0] != key:
+    if (cached is None or ver is None or cached[0] is not param or
+            cached[1] != (param.data_ptr(), ver, param.dtype, param.device)):
         w = param.detach().reshape(rows, cols)
         if w.dtype != dtype or not w.is_contiguous():
             w = w.to(dtype).contiguous()
-        cached = (key, w)
+        cached = (param, (param.data_ptr(), ver, param.dtype, param.device), w)
         object.__setattr__(module, attr, cached)
-    return cached[1]
+    return cached[2]
 
 
 def _check_cfg(dim, heads, dim_head):
@@ -122,6 +132,7 @@ class Attention(nn.Module):
             raise StreamCorrError(f"unknown GMA precision {self.precision!r}; choose 'f16' or 'f16x2'")
         if not fmap.is_cuda:
             raise StreamCorrError("Attention needs a CUDA tensor (no CPU fallback)")
+        _lib.require_no_grad("Attention", fmap, self.to_qk.weight)
         x = fmap.detach()
         if not x.is_contiguous():
             x = x.contiguous()
@@ -168,9 +179,13 @@ class Aggregate(nn.Module):
                                   f"{tuple(q.shape)} and {tuple(k.shape)}")
         if not q.is_cuda or q.device != k.device or q.dtype != k.dtype:
             raise StreamCorrError("Aggregate(q, k, fmap) needs q and k on the same CUDA device with the same dtype")
-        key = (q.data_ptr(), k.data_ptr(), q._version, k._version, tuple(q.shape), q.dtype, q.device, self.precision)
+        _lib.require_no_grad("Aggregate(q, k, fmap)", q, k)
+        vq, vk = _version_of(q), _version_of(k)
+        key = (q.data_ptr(), k.data_ptr(), vq, vk, tuple(q.shape), q.dtype, q.device, self.precision)
         cached = getattr(self, "_qk_cache", None)
-        if cached is not None and cached[0] == key:
+        # inference tensors carry no version counter: an in-place update could not be detected, so never reuse
+        if (cached is not None and vq is not None and vk is not None and cached[0] == key and
+                cached[1][0] is q and cached[1][1] is k):
             return cached[2]
         qc, kc = q.detach().contiguous(), k.detach().contiguous()
         P, d, h, w = qc.shape
@@ -205,6 +220,7 @@ class Aggregate(nn.Module):
         if fmap.dim() != 4 or tuple(fmap.shape) != (attn.P, self.dim, attn.h, attn.w):
             raise StreamCorrError(f"Aggregate expects fmap [{attn.P}, {self.dim}, {attn.h}, {attn.w}], "
                                   f"got {tuple(fmap.shape)}")
+        _lib.require_no_grad("Aggregate", fmap, self.to_v.weight, self.gamma)
         x = fmap.detach()
         if not x.is_contiguous():
             x = x.contiguous()

@@ -23,6 +23,7 @@ def upsample_flow(flow, mask, ratio=8):
     if tuple(mask.shape) != (N, 9 * ratio * ratio, H, W) or mask.device != flow.device:
         raise StreamCorrError(f"mask must be [{N}, {9 * ratio * ratio}, {H}, {W}] on the flow's device, "
                               f"got {tuple(mask.shape)}")
+    _lib.require_no_grad("upsample_flow", flow, mask)
     f = flow.detach()
     if f.dtype != torch.float32 or not f.is_contiguous():
         f = f.float().contiguous()

@@ -20,6 +20,8 @@ Cases
                     (8192 random positions per tensor + sums), inputs regenerated from seed
   gma_small.npz     Attention + Aggregate, heads=1, dim=dim_head=128, 12x16, P=2
   gma_proj.npz      heads=2, dim_head=32, dim=96 (project branch, core/gma.py:86-89,99-100)
+  upsample.npz      SKFlow_MF8.upsample_flow (core/models/streamflow.py:82-93), the reference METHOD itself, loaded
+                    through oracle/ref_model.py (timm shim): N=2, 6x7 -> 48x56, fp32 masks
 """
 import os
 import sys
@@ -140,7 +142,18 @@ def case_gma(name, heads, dim_head, dim, h, w, p, seed):
     np.savez_compressed(os.path.join(OUT, name), **out)
 
 
+def case_upsample():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import ref_model as rm
+    mod = rm.load_model_module("reference")
+    flow = rs_normal(40, (2, 2, 6, 7)) * np.float32(4.0)
+    mask = rs_normal(41, (2, 576, 6, 7)) * np.float32(2.0)
+    up = mod.SKFlow_MF8.upsample_flow(None, torch.from_numpy(flow), torch.from_numpy(mask), ratio=8)
+    np.savez_compressed(os.path.join(OUT, "upsample.npz"), flow=flow, mask=mask, out=up.numpy())
+
+
 if __name__ == "__main__":
+    case_upsample()
     case_corr_small()
     case_corr_batch()
     case_corr_cfg1()

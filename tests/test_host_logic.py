@@ -78,6 +78,12 @@ def _worker(rank, world, port, q):
         out = sfd.run_clips(clips, lambda c: c + 0.5)
         ok &= out.shape == (5 * (T - 1), 2, H, W)
         ok &= [float(out[i * (T - 1), 0, 0, 0]) for i in range(5)] == [c + 0.5 for c in range(5)]
+        # fewer clips than ranks: EVERY rank raises before any collective (no peer is left hanging in a gather)
+        try:
+            sfd.run_clips(clips[:1], lambda c: c)
+            ok = False
+        except ValueError:
+            pass
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -33,6 +33,30 @@ def test_upsample_flow_matches_reference(shape, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, 2e-3)])
+def test_upsample_flow_matches_reference_fixture(dtype, tol):
+    """tests/golden/upsample.npz was produced by the reference METHOD SKFlow_MF8.upsample_flow itself
+    (core/models/streamflow.py:82-93, loaded through oracle/ref_model.py by tests/golden/make_golden.py)."""
+    from streamflow_b200 import upsample_flow
+    from tests.helpers import load_golden
+    g = load_golden("upsample.npz")
+    flow, mask = torch.from_numpy(g["flow"]).cuda(), torch.from_numpy(g["mask"]).cuda().to(dtype)
+    got = upsample_flow(flow, mask).cpu()
+    want = torch.from_numpy(g["out"])
+    assert got.shape == want.shape
+    err = float((got - want).norm() / want.norm())
+    assert err < tol, f"rel err {err:.3e}"
+
+
+def test_upsample_fixture_agrees_with_the_restatement():
+    """CPU: the test-side restatement used for the larger GPU shapes equals the reference-generated fixture."""
+    from tests.helpers import load_golden
+    g = load_golden("upsample.npz")
+    want = ref_upsample(torch.from_numpy(g["flow"]), torch.from_numpy(g["mask"]))
+    np.testing.assert_allclose(want.numpy(), g["out"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
 def test_patch_upsample_replaces_method():
     from streamflow_b200 import patch_upsample
 
