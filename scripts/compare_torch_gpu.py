@@ -5,6 +5,7 @@ both sides (eager), plus a CUDA-graph replay of the full 12-iteration hot path f
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.set_grad_enabled(False)   # inference-only operators
 import bench
 import streamflow_b200 as sfb
 from oracle import torch_port as tp

@@ -6,6 +6,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.set_grad_enabled(False)   # inference-only operators
 import bench
 import streamflow_b200 as sfb
 

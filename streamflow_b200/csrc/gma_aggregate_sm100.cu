@@ -1,27 +1,39 @@
-// G3b: per-iteration GMA aggregation (core/gma.py:91-104), one kernel, no split-K:
+// G3b: per-iteration GMA aggregation (core/gma.py:91-104), one streaming kernel, no split-K, no separate projection:
 //
-//     out[p, c, n] = fmap[p, c, n] + (gamma / rowsum[p, n]) * sum_j V[p, c, j] * E[p, n, j]
+//     out[p, c, n] = fmap[p, c, n] + gamma * sum_c' W_v[c, c'] * ( sum_j X[p, c', j] * E[p, n, j] / rowsum[p, n] )
+//
+// i.e. the 1x1 `to_v` convolution is applied AFTER the attention-weighted sum (sum_j (W_v X)[c, j] E[n, j] =
+// (W_v (X E^T))[c, n]): the kernel streams the fp16 motion features X themselves (NCHW = K-major over keys, written
+// by gma_cast_kernel) through the big GEMM and applies W_v to the 128 x rows result with one extra small MMA per
+// CTA.  That removes the per-iteration v-projection launch (10.8-14.7 us of mma.sync work and a grid-wide
+// dependency in front of this kernel, 9 % of the round-1 step) and the fp16 rounding of V.
 //
 // HBM-bound on the fp16 softmax numerators E (297 MB per Sintel clip and iteration).  The GEMM is issued
-// TRANSPOSED -- D[channel, query] = V[channel, key] . E[query, key]^T, M = 128 channels, N = queries -- because the
+// TRANSPOSED -- Y[channel, query] = X[channel, key] . E[query, key]^T, M = 128 channels, N = queries -- because the
 // UMMA N extent is any multiple of 16 up to 256: the query rows of all maps are cut into 16-row units and every CTA
 // owns one contiguous range of units (the same count +-1 everywhere), for ALL key blocks.  Consequences:
 //   * every SM streams the same number of E bytes without split-K: no fp32 scratch accumulator, no atomics, no
 //     memset, no separate finalize pass, and the result is deterministic (one fp32 accumulator per output);
-//   * the accumulator comes out of TMEM channel-major (lane = channel, column = query), which is the NCHW layout
-//     of the result: the epilogue fuses the residual add and the softmax normalisation and writes `out` directly;
 //   * E is tile-major: 16 KB blocks of 128 queries x 64 keys, each block stored by gma_stats_kernel as the
 //     128B-swizzled K-major shared-memory image the UMMA descriptor expects, so a run of queries inside a block is
 //     contiguous in HBM and lands with ONE non-tensor bulk copy (cp.async.bulk); a row range touches at most 3
 //     blocks.  (Fetching the same rows as power-of-two TMA boxes cost 4-9 TMA instructions per key block and ran
 //     at half the speed: per-instruction TMA cost, not bytes, was the limit.)
-// Ring sizing: bulk copies of >= 16 KB saturate HBM with as few as 3 stages (scripts/probes/stream_probe.cu), so the
-// E ring simply takes the shared memory that the 3-stage V ring (16 KB per key block, L2 resident, evict_last) and the
-// prefetched fmap tile of the staged epilogue leave: 5 stages x 18 KB at Sintel size.  What does matter is the work
-// split: a CTA that straddles two maps runs the key loop twice (twice the V traffic and iterations for the same E
-// bytes) and was the tail of the whole kernel (98 us) until the split became per-map.
+// Epilogue (8 warps), per segment of <= 256 queries, in passes of `stage_rows` queries:
+//   1. Y leaves TMEM channel-major (lane = c', column = query); each value is normalised by 1 / rowsum[query]
+//      (a convex combination of X values: back in fp16 range), split into fp16 hi + lo (~22 bits) and written
+//      TRANSPOSED into a 128B-swizzled K-major staging tile [query][c'] -- the B operand of the second GEMM;
+//   2. one elected thread issues D2[c, query] = W_v[c, c'] . (hi + lo)[query, c']^T (16 tcgen05.mma of K = 16;
+//      W_v fp16, resident in shared memory since kernel start) INTO THE SAME TMEM COLUMNS the pass just drained;
+//   3. D2 leaves TMEM channel-major = NCHW, and `out = fmap + gamma * D2` is written directly.
+// A CTA with a single segment (Sintel / KITTI: 8-10 units per CTA) stages whole segments in the idle E / X rings and
+// prefetches its fmap tile there with cp.async while the second GEMM runs; multi-segment CTAs (Spring, batched
+// KITTI) keep a dedicated 32 KB staging tile so the epilogue of segment i overlaps the key loop of segment i + 1.
+// Ring sizing: bulk copies of >= 16 KB saturate HBM with as few as 3 stages (scripts/probes/stream_probe.cu).  What
+// does matter is the work split: a CTA that straddles two maps runs the key loop twice (twice the X traffic and
+// iterations for the same E bytes) and was the tail of the whole kernel (98 us) until the split became per-map.
 //
-// warps: 0 = E producer (bulk copies), 1 = TMEM alloc + MMA issuer, 2 = V producer (TMA), 3-10 = epilogue.
+// warps: 0 = E producer (bulk copies), 1 = TMEM alloc + MMA issuer, 2 = W_v + X producer (TMA), 3-10 = epilogue.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -36,7 +48,8 @@ constexpr int BK = 64, kCh = 128;
 constexpr int kUnit = 16;                                   // query rows per work unit (UMMA N granularity at M=128)
 constexpr int kMaxUnits = 16;                               // 256 rows = the UMMA N limit
 constexpr int kMaxEStages = 12, kVStages = 3;
-constexpr int kVBytes = kCh * BK * 2;                       // 16 KB
+constexpr int kVBytes = kCh * BK * 2;                       // 16 KB: one key block of X (128 channels x 64 keys)
+constexpr int kWBytes = 2 * kVBytes;                        // 32 KB: W_v [c][c'] fp16 as two 64-wide k-blocks
 constexpr int kSmemBytes = 227 * 1024;                      // everything the SM has
 constexpr int kBarBytes = 512;
 constexpr int kRing = (kSmemBytes - 1024 /*align slack*/ - kBarBytes) / 1024 * 1024;
@@ -45,12 +58,15 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = (3 + kEpiWarps) * 32;
 
 struct GmaAggArgs {
-    CUtensorMap tm_v;
+    CUtensorMap tm_v;               // X16 [P, 128, Npad] fp16
+    CUtensorMap tm_w;               // W_v [128, 128] fp16
     GmaAggParams p;
     int units_per_map;              // ceil(N / 16)
     int e_stages, e_stage_bytes;    // E stage = the rows of the longest segment
-    int fbuf_pitch;                 // > 0: the fmap tile of the CTA's single segment is prefetched into shared memory
-    int fbuf_off, rbuf_off;         // byte offsets of that tile and of its rscale row inside the ring
+    int x_off, w_off;               // byte offsets of the X ring and of W_v inside the ring area
+    int stage_off, stage_rows;      // staging tile of the second GEMM: 4 sub-tiles [hi|lo][k-block] of stage_rows x 128 B
+    int fbuf_pitch;                 // > 0: single-segment CTAs; the fmap tile is prefetched into shared memory
+    int fbuf_off;                   // byte offset of that tile inside the ring area
 };
 
 struct Seg {
@@ -70,54 +86,50 @@ __device__ __forceinline__ bool next_seg(long long& u, long long u_end, int upm,
     return true;
 }
 
+// 16 fmap values of one channel (zero past N)
 template <typename T>
-__device__ __forceinline__ void load_chunk(const T* fm, const float* rs, int n0, int N, bool vec, float (&f)[16],
-                                           float (&r)[16]) {
+__device__ __forceinline__ void load_chunk(const T* fm, int n0, int N, bool vec, float (&f)[16]) {
     if constexpr (sizeof(T) == 4) {
         if (vec) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                if (n0 + 4 * j < N) {
-                    a = *reinterpret_cast<const float4*>(fm + 4 * j);
-                    b = __ldg(reinterpret_cast<const float4*>(rs + 4 * j));
-                }
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n0 + 4 * j < N) a = *reinterpret_cast<const float4*>(fm + 4 * j);
                 f[4 * j] = a.x; f[4 * j + 1] = a.y; f[4 * j + 2] = a.z; f[4 * j + 3] = a.w;
-                r[4 * j] = b.x; r[4 * j + 1] = b.y; r[4 * j + 2] = b.z; r[4 * j + 3] = b.w;
             }
             return;
         }
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const bool ok = n0 + j < N;
-        f[j] = ok ? static_cast<float>(fm[j]) : 0.f;
-        r[j] = ok ? __ldg(rs + j) : 0.f;
-    }
+    for (int j = 0; j < 16; ++j) f[j] = (n0 + j < N) ? static_cast<float>(fm[j]) : 0.f;
 }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-// out[n0 .. n0+16) = fmap + acc * rscale for one channel; `vec`: N % 4 == 0, so float4 stores never straddle N
+// out[n0 .. n0+16) = fmap + gamma * acc for one channel; `vec`: N % 4 == 0, so float4 stores never straddle N
 __device__ __forceinline__ void store_chunk(float* out, int n0, int N, bool vec, const uint32_t (&v)[16],
-                                            const float (&f)[16], const float (&r)[16]) {
+                                            const float (&f)[16], float g) {
     if (vec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (n0 + 4 * j < N)
                 __stcs(reinterpret_cast<float4*>(out + n0 + 4 * j),
-                       make_float4(fmaf(__uint_as_float(v[4 * j]), r[4 * j], f[4 * j]),
-                                   fmaf(__uint_as_float(v[4 * j + 1]), r[4 * j + 1], f[4 * j + 1]),
-                                   fmaf(__uint_as_float(v[4 * j + 2]), r[4 * j + 2], f[4 * j + 2]),
-                                   fmaf(__uint_as_float(v[4 * j + 3]), r[4 * j + 3], f[4 * j + 3])));
+                       make_float4(fmaf(__uint_as_float(v[4 * j]), g, f[4 * j]),
+                                   fmaf(__uint_as_float(v[4 * j + 1]), g, f[4 * j + 1]),
+                                   fmaf(__uint_as_float(v[4 * j + 2]), g, f[4 * j + 2]),
+                                   fmaf(__uint_as_float(v[4 * j + 3]), g, f[4 * j + 3])));
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (n0 + j < N) out[n0 + j] = fmaf(__uint_as_float(v[j]), r[j], f[j]);
+            if (n0 + j < N) out[n0 + j] = fmaf(__uint_as_float(v[j]), g, f[j]);
     }
+}
+
+__device__ __forceinline__ void epi_bar_sync() {       // the 8 epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
 }
 
 template <typename T>
@@ -126,8 +138,9 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     // align by pointer arithmetic (not through an integer) so the compiler keeps the shared address space: STS / LDS
     // instead of generic ST / LD in the epilogue
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* e_base = smem;
-    uint8_t* v_base = smem + kRing - kVStages * kVBytes;     // [E ring | fmap tile + rscale (optional) | V ring | barriers]
+    uint8_t* e_base = smem;                                  // [E ring | (staging tile) | X ring | W_v | barriers]
+    uint8_t* v_base = smem + args.x_off;
+    uint8_t* w_base = smem + args.w_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRing);
     uint64_t* e_full = bars;
     uint64_t* e_empty = e_full + kMaxEStages;
@@ -135,7 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     uint64_t* v_empty = v_full + kVStages;
     uint64_t* tfull = v_empty + kVStages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* w_full = tempty + 2;
+    uint64_t* d2_full = w_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_full + 1);
+    float* gamma_s = reinterpret_cast<float*>(tmem_slot + 1);
 
     const GmaAggParams& p = args.p;
     // warp index through a shuffle so the compiler knows the role dispatch is warp-uniform (see gma_sm100.cu)
@@ -145,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     const int e_stages = args.e_stages;
     // Work split.  With at least one CTA per map, every map gets floor(G / P) or one more CTAs and each CTA a
     // contiguous run of that map's units: no CTA straddles two maps (a straddler would run the key loop twice --
-    // twice the V traffic and iterations for the same E bytes -- and become the tail of the kernel).
+    // twice the X traffic and iterations for the same E bytes -- and become the tail of the kernel).
     long long u_begin, u_end;
     {
         const int G = gridDim.x, bid = blockIdx.x;
@@ -174,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&args.tm_v);
+        tma_prefetch_desc(&args.tm_w);
         for (int i = 0; i < kMaxEStages; ++i) {
             mbar_init(&e_full[i], 1);
             mbar_init(&e_empty[i], 1);
@@ -186,6 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], kEpiWarps);
         }
+        mbar_init(w_full, 1);
+        mbar_init(d2_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -235,7 +254,13 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             }
         }
     } else if (warp == 2) {
-        {                                                      // ---- V producer
+        {                                                      // ---- W_v (once) + X producer
+            if (elect_one()) {
+                mbar_expect_tx(w_full, kWBytes);
+                tma_load_3d_hint(&args.tm_w, w_full, w_base, 0, 0, 0, kEvictLast);
+                tma_load_3d_hint(&args.tm_w, w_full, w_base + kVBytes, BK, 0, 0, kEvictLast);
+            }
+            __syncwarp();
             int stage = 0;
             uint32_t phase = 0;
             long long u = u_begin;
@@ -297,48 +322,111 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     } else {                                                   // ---- epilogue (warps 3-10)
         const int quad = warp & 3;                             // TMEM lane quadrant this warp may read
         const int sub = (warp - 3) >> 2;                       // which half of the 16-column chunks
-        const int ch = quad * 32 + lane;                       // channel = TMEM lane
+        const int ch = quad * 32 + lane;                       // channel = TMEM lane (c' of Y, then c of D2)
+        const int et = static_cast<int>(threadIdx.x) - 96;     // 0 .. 255
+        if (et == 0) *gamma_s = __ldg(p.gamma);                // ONE read of the scalar per CTA (visible after epi_bar_sync)
+        const bool single = args.fbuf_pitch > 0;
+        const bool vec = (p.N & 3) == 0;
+        uint8_t* stage = smem + args.stage_off;
+        const int SR = args.stage_rows;
+        const uint32_t sub_bytes = static_cast<uint32_t>(SR) * 128u;      // one [query][64 x c'] sub-tile
+        // staging address of (row, ch): 128-byte rows, 16-byte chunk (ch & 63) >> 3 of row r stored at chunk ^ (r & 7)
+        const uint32_t st_kb = static_cast<uint32_t>(ch >> 6) * sub_bytes;
+        const uint32_t st_chunk = static_cast<uint32_t>((ch & 63) >> 3), st_in = static_cast<uint32_t>(ch & 7) * 2u;
+        uint32_t d2_phase = 0;
+        bool w_ready = false;
         int local = 0;
         long long u = u_begin;
         Seg s;
-        if (args.fbuf_pitch > 0) {
-            // Single-segment CTA: the epilogue is the un-overlapped tail of the kernel, so everything it reads from
-            // global memory (the fmap tile, its rscale row) is fetched into shared memory while the key loop runs.
-            if (next_seg(u, u_end, upm, s)) {
-                uint8_t* fbuf = smem + args.fbuf_off;
-                float* rbuf = reinterpret_cast<float*>(smem + args.rbuf_off);
-                const int t = threadIdx.x - 96;
+        while (next_seg(u, u_end, upm, s)) {
+            const int acc = local & 1;
+            const int chunks = s.rows / 16;
+            const long long base = (static_cast<long long>(s.pb) * kCh + ch) * p.N;
+            const T* fm = reinterpret_cast<const T*>(p.fmap) + base;
+            const float* rsum = p.rowsum + static_cast<long long>(s.pb) * p.N;
+            float* out = p.out + base;
+            uint8_t* fbuf = smem + args.fbuf_off;
+            mbar_wait(&tfull[acc], (local >> 1) & 1);          // every MMA of the key loop is done: the rings are idle
+            tc_fence_after();
+            if (single) {
+                // the un-overlapped tail of the kernel: fetch the fmap tile into the idle ring while the second GEMM runs
                 const int valid = min(s.rows, p.N - s.row0);
                 const int cpr = valid * static_cast<int>(sizeof(T)) / 16;         // 16-byte chunks per channel row
                 const T* fm0 = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(s.pb) * kCh * p.N + s.row0;
-                for (int i = t; i < kCh * cpr; i += kEpiWarps * 32) {
+                for (int i = et; i < kCh * cpr; i += kEpiWarps * 32) {
                     const int c = i / cpr, k = i - c * cpr;
                     cp_async16(fbuf + c * args.fbuf_pitch + k * 16,
                                reinterpret_cast<const uint8_t*>(fm0 + static_cast<long long>(c) * p.N) + k * 16);
                 }
-                const float* rs = p.rscale + static_cast<long long>(s.pb) * p.N + s.row0;
-                for (int i = t; i < valid / 4; i += kEpiWarps * 32) cp_async16(rbuf + 4 * i, rs + 4 * i);
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-
-                float* out = p.out + (static_cast<long long>(s.pb) * kCh + ch) * p.N;
-                const uint8_t* frow = fbuf + ch * args.fbuf_pitch;
-                const int chunks = s.rows / 16;
-                mbar_wait(&tfull[0], 0);
+            }
+            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+#pragma unroll 1
+            for (int q0 = 0; q0 < s.rows; q0 += SR) {          // ---- second GEMM, `SR` queries per pass
+                const int w = min(SR, s.rows - q0);
+#pragma unroll 1
+                for (int cc = sub; cc < w / 16; cc += 2) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_acc + q0 + cc * 16, v);
+                    float ri[16];
+                    const int n0 = s.row0 + q0 + cc * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ri[j] = (n0 + j < p.N) ? __frcp_rn(__ldg(rsum + n0 + j)) : 0.f;
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float y = (n0 + j < p.N) ? __uint_as_float(v[j]) * ri[j] : 0.f;
+                        const __half hi = __float2half_rn(y);
+                        const __half lo = __float2half_rn(y - __half2float(hi));
+                        const uint32_t r = static_cast<uint32_t>(cc * 16 + j);
+                        const uint32_t off = st_kb + r * 128u + ((st_chunk ^ (r & 7u)) << 4) + st_in;
+                        *reinterpret_cast<__half*>(stage + off) = hi;
+                        *reinterpret_cast<__half*>(stage + 2u * sub_bytes + off) = lo;
+                    }
+                }
+                fence_proxy_async_smem();                       // staging writes -> visible to the tensor core (async proxy)
+                tc_fence_before();                              // the TMEM reads of this pass precede the MMA that overwrites them
+                epi_bar_sync();
+                if (warp == 3) {
+                    if (!w_ready) {
+                        mbar_wait(w_full, 0);
+                        w_ready = true;
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t idesc = make_idesc_f16_f32(kCh, w);
+                        const uint32_t d_tmem = tmem_base + acc * 256 + q0;
+#pragma unroll
+                        for (int part = 0; part < 2; ++part)            // hi, lo
+#pragma unroll
+                            for (int kb2 = 0; kb2 < 2; ++kb2) {         // c' 0-63, 64-127
+                                const uint64_t da = make_kmajor_sw128_desc(smem_u32(w_base + kb2 * kVBytes));
+                                const uint64_t db =
+                                    make_kmajor_sw128_desc(smem_u32(stage + (part * 2 + kb2) * sub_bytes));
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (part | kb2 | k) != 0);
+                            }
+                        umma_commit(d2_full);
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(d2_full, d2_phase);                   // D2 columns written, staging tile free again
+                d2_phase ^= 1;
                 tc_fence_after();
-                const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+            }
+            const float g = *gamma_s;
+            if (single) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                epi_bar_sync();                                 // every thread's part of the fmap tile has landed
+                const uint8_t* frow = fbuf + ch * args.fbuf_pitch;
+                const int valid = min(s.rows, p.N - s.row0);
 #pragma unroll 1
                 for (int c = sub; c < chunks; c += 2) {
                     uint32_t v[16];
                     tmem_ld_32x16(t_acc + c * 16, v);
-                    float f[16], r[16];
+                    float f[16];
                     if (c * 16 < valid) {      // chunks past N are never stored
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b = *reinterpret_cast<const float4*>(rbuf + c * 16 + 4 * j);
-                            r[4 * j] = b.x; r[4 * j + 1] = b.y; r[4 * j + 2] = b.z; r[4 * j + 3] = b.w;
-                        }
                         if constexpr (sizeof(T) == 4) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -354,37 +442,23 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
                         }
                     }
                     tmem_ld_wait();
-                    store_chunk(out, s.row0 + c * 16, p.N, true, v, f, r);
+                    store_chunk(out, s.row0 + c * 16, p.N, true, v, f, g);
                 }
-            }
-        } else {
-        const bool vec = (p.N & 3) == 0;
-        while (next_seg(u, u_end, upm, s)) {
-            const int acc = local & 1;
-            const int chunks = s.rows / 16;
-            const long long base = (static_cast<long long>(s.pb) * kCh + ch) * p.N;
-            const T* fm = reinterpret_cast<const T*>(p.fmap) + base;
-            const float* rs = p.rscale + static_cast<long long>(s.pb) * p.N;
-            float* out = p.out + base;
-            float f[16], r[16];
-            if (sub < chunks) load_chunk<T>(fm + s.row0 + sub * 16, rs + s.row0 + sub * 16, s.row0 + sub * 16, p.N, vec, f, r);
-            mbar_wait(&tfull[acc], (local >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+            } else {
+                float f[16];
+                if (sub < chunks) load_chunk<T>(fm + s.row0 + sub * 16, s.row0 + sub * 16, p.N, vec, f);
 #pragma unroll 1
-            for (int c = sub; c < chunks; c += 2) {
-                uint32_t v[16];
-                tmem_ld_32x16(t_acc + c * 16, v);
-                float fn[16], rn[16];
-                const int n0 = s.row0 + c * 16;
-                if (c + 2 < chunks) load_chunk<T>(fm + n0 + 32, rs + n0 + 32, n0 + 32, p.N, vec, fn, rn);
-                tmem_ld_wait();
-                store_chunk(out, n0, p.N, vec, v, f, r);
-                if (c + 2 < chunks) {
+                for (int c = sub; c < chunks; c += 2) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(t_acc + c * 16, v);
+                    float fn[16];
+                    const int n0 = s.row0 + c * 16;
+                    if (c + 2 < chunks) load_chunk<T>(fm + n0 + 32, n0 + 32, p.N, vec, fn);
+                    tmem_ld_wait();
+                    store_chunk(out, n0, p.N, vec, v, f, g);
+                    if (c + 2 < chunks) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        f[j] = fn[j];
-                        r[j] = rn[j];
+                        for (int j = 0; j < 16; ++j) f[j] = fn[j];
                     }
                 }
             }
@@ -392,7 +466,6 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
             ++local;
-        }
         }
     }
 
@@ -416,9 +489,11 @@ int launch_typed(const GmaAggArgs& args, int grid, cudaStream_t s) {
 
 }  // namespace
 
-int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num_sms, cudaStream_t s) {
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_w, int num_sms,
+                         cudaStream_t s) {
     GmaAggArgs args;
-    args.tm_v = tm_v;
+    args.tm_v = tm_x;
+    args.tm_w = tm_w;
     args.p = p;
     args.units_per_map = (p.N + kUnit - 1) / kUnit;
     const long long U = static_cast<long long>(p.P) * args.units_per_map;
@@ -428,20 +503,38 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num
     args.e_stage_bytes = seg_units * kUnit * 128;
     const int elt = (p.fmap_dtype == SF_DT_F32) ? 4 : 2;
     const int rows_cap = seg_units * kUnit;
-    int avail = kRing - kVStages * kVBytes;
-    // staged epilogue: one segment per CTA, 16-byte aligned fmap rows, and room for at least 4 E stages next to the tile
+    args.w_off = kRing - kWBytes;
+    args.x_off = args.w_off - kVStages * kVBytes;
+    // Single-segment CTAs (one segment per CTA needs the per-map split, i.e. P <= grid, and 16-byte aligned fmap rows):
+    // after the key loop the E and X rings are idle, so the staging tile of the second GEMM (whole segment if it fits)
+    // and the prefetched fmap tile live there and the E ring keeps every byte during the loop.
     args.fbuf_pitch = 0;
-    args.fbuf_off = args.rbuf_off = 0;
-    const int fbuf_bytes = (kCh * (rows_cap * elt + 16) + rows_cap * 4 + 1023) / 1024 * 1024;
-    // (one segment per CTA needs the per-map split, i.e. P <= grid: a linear split may straddle two maps)
-    if (p.P <= grid && per_cta <= kMaxUnits && (static_cast<long long>(p.N) * elt) % 16 == 0 &&
-        (reinterpret_cast<uintptr_t>(p.fmap) & 15) == 0 && avail - fbuf_bytes >= 4 * args.e_stage_bytes) {
-        args.fbuf_pitch = rows_cap * elt + 16;
-        avail -= fbuf_bytes;
-        args.fbuf_off = avail;
-        args.rbuf_off = avail + kCh * args.fbuf_pitch;
+    args.fbuf_off = 0;
+    bool single = p.P <= grid && per_cta <= kMaxUnits && (static_cast<long long>(p.N) * elt) % 16 == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.fmap) & 15) == 0;
+    int e_avail = 0;
+    if (single) {
+        const int pitch = rows_cap * elt + 16;
+        const int fbuf_bytes = kCh * pitch;
+        int sr = rows_cap;
+        while (sr > 16 && 512 * sr + fbuf_bytes > args.w_off) sr -= 16;
+        if (512 * sr + fbuf_bytes > args.w_off) {
+            single = false;
+        } else {
+            args.stage_rows = sr;
+            args.stage_off = 0;
+            args.fbuf_pitch = pitch;
+            args.fbuf_off = 512 * sr;
+            e_avail = args.x_off;
+        }
     }
-    args.e_stages = std::min(kMaxEStages, avail / args.e_stage_bytes);
+    if (!single) {      // dedicated staging tile: the epilogue of one segment overlaps the key loop of the next
+        args.stage_rows = 64;
+        args.stage_off = args.x_off - 512 * args.stage_rows;
+        e_avail = args.stage_off;
+    }
+    args.e_stages = std::min(kMaxEStages, e_avail / args.e_stage_bytes);
+    SF_REQUIRE(args.e_stages >= 2, "gma_aggregate: internal error, E ring of %d stages", args.e_stages);
     switch (p.fmap_dtype) {
         case SF_DT_F32: return launch_typed<float>(args, grid, s);
         case SF_DT_F16: return launch_typed<__half>(args, grid, s);

@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, rowsum_fx_off, v_off, rscale_off, eye_off, total;
+    int64_t q_off, k_off, rowmax_off, rowsum_fx_off, x16_off, w16_off, eye_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -19,8 +19,8 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.k_off = off;       off += align_up(P * N * ws.Kp * 2, 1024);
     ws.rowmax_off = off;  off += align_up(P * N * 4, 1024);
     ws.rowsum_fx_off = off;  off += align_up(P * N * 8, 1024);
-    ws.v_off = off;       off += align_up(P * d * ws.Npad * 2, 1024);
-    ws.rscale_off = off;  off += align_up(P * N * 4, 1024);
+    ws.x16_off = off;     off += align_up(P * d * ws.Npad * 2, 1024);
+    ws.w16_off = off;     off += align_up(d * d * 2, 1024);
     ws.eye_off = off;     off += align_up(d * d * 4, 1024);
     ws.total = off;
     return ws;
@@ -158,35 +158,31 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     uint8_t* wsb = static_cast<uint8_t*>(workspace);
     const int64_t Npad = ws.Npad;
 
-    GmaProjParams pv{};
     SF_REQUIRE(w_dtype == SF_DT_F32 || w_dtype == SF_DT_F16, "gma_aggregate: w_v must be fp32 or fp16");
-    pv.x = fmap; pv.x_dtype = fmap_dtype;
-    pv.w = (w_dtype == SF_DT_F32) ? static_cast<const float*>(w_v) : nullptr;
-    pv.w16 = (w_dtype == SF_DT_F16) ? static_cast<const __half*>(w_v) : nullptr;
-    pv.P = (int)P; pv.C = (int)C; pv.N = (int)N; pv.O = 128;
-    pv.scale = 1.0f;
-    pv.out = reinterpret_cast<__half*>(wsb + ws.v_off);
-    pv.out_batch_stride = d * Npad; pv.ld = (int)Npad; pv.token_major = 0; pv.split = 0; pv.is_b = 0;
-    pv.rowsum = rowsum; pv.gamma = gamma; pv.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
+    __half* x16 = reinterpret_cast<__half*>(wsb + ws.x16_off);
+    __half* w16 = reinterpret_cast<__half*>(wsb + ws.w16_off);
     const int parts = debug_gma_mask();
     if (parts & 1)
-        if (int rc = (w_dtype == SF_DT_F16) ? launch_gma_proj_v(pv, s) : launch_gma_proj(pv, s)) return rc;
+        if (int rc = launch_gma_cast(fmap, fmap_dtype, x16, P * C, N, Npad, w_v, w_dtype, w16, d * C, s)) return rc;
 
-    CUtensorMap tm_v;
+    CUtensorMap tm_x, tm_w;
     const int64_t e_rows = (N + 127) / 128 * (Npad / 64) * 128;       // 128-byte rows of tile-major E per map
-    if (int rc = make_tmap3(&tm_v, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.v_off, Npad, d, P, Npad * 2,
-                            d * Npad * 2, 64, 128, "V"))
+    if (int rc = make_tmap3(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, x16, Npad, C, P, Npad * 2, C * Npad * 2, 64, 128,
+                            "X16"))
+        return rc;
+    if (int rc = make_tmap3(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, w16, C, d, 1, C * 2, d * C * 2, 64, 128, "Wv"))
         return rc;
 
     GmaAggParams ap{};
     ap.P = (int)P; ap.N = (int)N; ap.Npad = (int)Npad; ap.C = (int)C;
     ap.k_blocks = (int)(Npad / 64);
-    ap.rscale = reinterpret_cast<float*>(wsb + ws.rscale_off);
+    ap.rowsum = rowsum;
+    ap.gamma = gamma;
     ap.fmap = fmap; ap.fmap_dtype = fmap_dtype;
     ap.out = out;
     ap.e_ptr = static_cast<const __half*>(E);
     ap.e_map_stride = e_rows * 64;
-    return (parts & 2) ? launch_gma_aggregate(ap, tm_v, di.sms, s) : SF_OK;
+    return (parts & 2) ? launch_gma_aggregate(ap, tm_x, tm_w, di.sms, s) : SF_OK;
 }
 
 }  // extern "C"

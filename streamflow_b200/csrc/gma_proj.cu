@@ -75,10 +75,6 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
 
     pdl_launch();
     pdl_wait();
-    if (p.rscale != nullptr && tid < kTok && n0 + tid < p.N) {
-        const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
-        p.rscale[r] = __ldg(p.gamma) / __ldg(p.rowsum + r);
-    }
     if (!second && tid < kTok && n0 + tid < p.N) {
         const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
         if (p.zero_u32 != nullptr) p.zero_u32[r] = 0u;
@@ -232,106 +228,52 @@ __global__ void __launch_bounds__(256, 2) gma_proj_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// v projection, every refinement iteration: out[p, o, n] = fp16(sum_c W16[o, c] * X[p, c, n]), channel-major with
-// pitch ld = Npad (pad columns zero).  Weights arrive already in fp16 (cached by the caller, they never change
-// during inference) and go straight to shared memory with cp.async; a CTA covers 128 tokens so the whole
-// projection is one wave of 165 CTAs at Sintel size (2 CTAs / SM).  Also writes rscale = gamma / rowsum.
-constexpr int kTokV = 128;
-constexpr int kXPadV = kTokV + 8;      // 272 B rows: ldmatrix conflict-free
-
+// Operand preparation of the aggregate, every refinement iteration: the motion features X [rows = P * C][N] (fp32 in
+// the model, core/update.py:339) -> fp16 [rows][Npad] with zero pad columns -- the K-major-over-keys A operand that
+// gma_aggregate_kernel streams by TMA -- and W_v -> fp16 (the reference's autocast casts both the same way,
+// core/gma.py:94 under streamflow.py:135).  Pure streaming: 8 elements per thread, 16-byte stores.
 template <typename T>
-__global__ void __launch_bounds__(256, 2) gma_proj_v_kernel(const __grid_constant__ GmaProjParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int C = 128, wpad = C + 8;
-    __half* Xs = reinterpret_cast<__half*>(smem);                    // [C][kXPadV]
-    __half* Ws = Xs + C * kXPadV;                                    // [128][wpad]
-    __half* Ds = Ws + 128 * wpad;                                    // [128][kXPadV]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n0 = blockIdx.x * kTokV;
-    const int pb = blockIdx.y;
+__global__ void __launch_bounds__(256) gma_cast_kernel(const T* __restrict__ x, __half* __restrict__ x16, int N, int Npad,
+                                                       int blocks_per_row, long long x_blocks, const void* w,
+                                                       int w_is_f32, __half* __restrict__ w16, int w_elems) {
     pdl_launch();
-    // weights do not depend on the previous kernel: start their copy before waiting for it
-    for (int i = tid; i < 128 * (C / 8); i += 256) {
-        const int o = i >> 4, seg = i & 15;
-        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(Ws + o * wpad + seg * 8));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(p.w16 + o * C + seg * 8) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
     pdl_wait();
-    if (p.rscale != nullptr && tid < kTokV && n0 + tid < p.N) {
-        const long long r = static_cast<long long>(pb) * p.N + n0 + tid;
-        p.rscale[r] = __ldg(p.gamma) / __ldg(p.rowsum + r);
-    }
-    const T* X = reinterpret_cast<const T*>(p.x) + static_cast<long long>(pb) * C * p.N;
-    const bool vec_ok = (sizeof(T) == 4) && ((p.N & 3) == 0) && (n0 + kTokV <= p.N) &&
-                        ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const long long b = blockIdx.x;
+    if (b >= x_blocks) {                                             // trailing blocks: the weights
+        const int i = (static_cast<int>(b - x_blocks) * 256 + threadIdx.x) * 8;
+        if (i < w_elems) {
+            alignas(16) __half h[8];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {                           // 2 x 8 float4 per thread
-        float v[8][4];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = tid + (half * 8 + u) * 256;                // 0 .. C*32-1
-            const int c = i >> 5, n4 = (i & 31) * 4;
-            if (vec_ok) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(
-                    reinterpret_cast<const float*>(X) + static_cast<long long>(c) * p.N + n0 + n4));
-                v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int n = n0 + n4 + e;
-                    v[u][e] = (n < p.N) ? load_as_float<T>(X + static_cast<long long>(c) * p.N + n) : 0.f;
-                }
-            }
+            for (int e = 0; e < 8; ++e)
+                h[e] = w_is_f32 ? __float2half_rn(static_cast<const float*>(w)[i + e]) : static_cast<const __half*>(w)[i + e];
+            *reinterpret_cast<uint4*>(w16 + i) = *reinterpret_cast<const uint4*>(h);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = tid + (half * 8 + u) * 256;
-            const int c = i >> 5, n4 = (i & 31) * 4;
-            __half2* d = reinterpret_cast<__half2*>(Xs + c * kXPadV + n4);
-            d[0] = __floats2half2_rn(v[u][0], v[u][1]);
-            d[1] = __floats2half2_rn(v[u][2], v[u][3]);
+        return;
+    }
+    const long long row = b / blocks_per_row;
+    const int n0 = (static_cast<int>(b - row * blocks_per_row) * 256 + threadIdx.x) * 8;
+    if (n0 >= Npad) return;
+    const T* src = x + row * N;
+    float v[8];
+    bool done = false;
+    if constexpr (sizeof(T) == 4) {
+        if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a = (n0 < N) ? __ldcs(reinterpret_cast<const float4*>(src + n0)) : z;
+            const float4 c = (n0 + 4 < N) ? __ldcs(reinterpret_cast<const float4*>(src + n0 + 4)) : z;
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            done = true;
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-    float acc[16][4] = {};
-    const int g = lane >> 2, t = lane & 3;
-    const __half* wrow = Ws + (warp * 16 + g) * wpad;
-#pragma unroll 2
-    for (int k0 = 0; k0 < C; k0 += 16) {
-        unsigned a[4];
-        a[0] = *reinterpret_cast<const unsigned*>(wrow + k0 + 2 * t);
-        a[1] = *reinterpret_cast<const unsigned*>(wrow + 8 * wpad + k0 + 2 * t);
-        a[2] = *reinterpret_cast<const unsigned*>(wrow + k0 + 8 + 2 * t);
-        a[3] = *reinterpret_cast<const unsigned*>(wrow + 8 * wpad + k0 + 8 + 2 * t);
+    if (!done) {
 #pragma unroll
-        for (int jt = 0; jt < 16; jt += 2) {
-            const int mat = lane >> 3, r = lane & 7;
-            const __half* src = Xs + (k0 + (mat & 1) * 8 + r) * kXPadV + (jt + (mat >> 1)) * 8;
-            unsigned b0, b1, b2, b3;
-            ldmatrix_x4_trans(b0, b1, b2, b3, src);
-            mma_16816(acc[jt], a, b0, b1);
-            mma_16816(acc[jt + 1], a, b2, b3);
-        }
+        for (int e = 0; e < 8; ++e) v[e] = (n0 + e < N) ? load_as_float<T>(src + n0 + e) : 0.f;
     }
-    // D fragment: acc[jt][0..1] -> (o = 16w + g, n = 8jt + 2t, +1); acc[jt][2..3] -> o + 8
+    alignas(16) __half2 h[4];
 #pragma unroll
-    for (int jt = 0; jt < 16; ++jt) {
-        const int o = warp * 16 + g, n = jt * 8 + 2 * t;
-        *reinterpret_cast<__half2*>(Ds + o * kXPadV + n) = __floats2half2_rn(acc[jt][0], acc[jt][1]);
-        *reinterpret_cast<__half2*>(Ds + (o + 8) * kXPadV + n) = __floats2half2_rn(acc[jt][2], acc[jt][3]);
-    }
-    __syncthreads();
-    __half* out = p.out + static_cast<long long>(pb) * p.out_batch_stride;
-    for (int i = tid; i < 128 * 16; i += 256) {                      // 128 tokens = 256 B per output row
-        const int o = i >> 4, seg = i & 15;
-        if (n0 + seg * 8 < p.ld)
-            *reinterpret_cast<int4*>(out + static_cast<long long>(o) * p.ld + n0 + seg * 8) =
-                *reinterpret_cast<const int4*>(Ds + o * kXPadV + seg * 8);
-    }
+    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(x16 + row * Npad + n0) = *reinterpret_cast<const uint4*>(h);
 }
 
 }  // namespace
@@ -362,25 +304,29 @@ int launch_gma_proj(const GmaProjParams& p, cudaStream_t s) {
     }
 }
 
-int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s) {
-    SF_REQUIRE(p.O == 128 && p.C == 128, "gma_proj_v: specialised for 128 -> 128 channels");
-    SF_REQUIRE(p.ld % 8 == 0 && p.w16 != nullptr && (reinterpret_cast<uintptr_t>(p.w16) & 15) == 0,
-               "gma_proj_v: bad output pitch or fp16 weight pointer");
-    const int smem = (2 * 128 * kXPadV + 128 * (128 + 8)) * 2;
-    dim3 grid((p.ld + kTokV - 1) / kTokV, p.P);
-    auto launch = [&](auto kernel) -> int {
-        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
+int launch_gma_cast(const void* x, int x_dtype, __half* x16, int64_t rows, int64_t N, int64_t Npad, const void* w,
+                    int w_dtype, __half* w16, int64_t w_elems, cudaStream_t s) {
+    SF_REQUIRE(Npad % 8 == 0 && w_elems % 8 == 0, "gma_cast: Npad and the weight count must be multiples of 8");
+    SF_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w16) & 15) == 0,
+               "gma_cast: outputs must be 16-byte aligned");
+    const int bpr = static_cast<int>((Npad + 2047) / 2048);
+    const long long x_blocks = rows * bpr;
+    const long long w_blocks = (w_elems + 2047) / 2048;
+    SF_REQUIRE(x_blocks + w_blocks < (1ll << 31), "gma_cast: shape too large");
+    const dim3 grid(static_cast<unsigned>(x_blocks + w_blocks));
+    auto launch = [&](auto kernel, auto* xp) -> int {
         prof_before(SF_KERNEL_GMA_PROJ, s);
-        SF_CUDA_CHECK(launch_kernel(kernel, grid, dim3(256), static_cast<size_t>(smem), s, p));
+        SF_CUDA_CHECK(launch_kernel(kernel, grid, dim3(256), 0, s, xp, x16, static_cast<int>(N), static_cast<int>(Npad), bpr,
+                                    x_blocks, w, static_cast<int>(w_dtype == SF_DT_F32), w16, static_cast<int>(w_elems)));
         prof_after(SF_KERNEL_GMA_PROJ, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;
     };
-    switch (p.x_dtype) {
-        case SF_DT_F32: return launch(gma_proj_v_kernel<float>);
-        case SF_DT_F16: return launch(gma_proj_v_kernel<__half>);
-        case SF_DT_BF16: return launch(gma_proj_v_kernel<__nv_bfloat16>);
-        default: set_error("gma_proj_v: unsupported dtype %d", p.x_dtype); return SF_ERR_INVALID;
+    switch (x_dtype) {
+        case SF_DT_F32: return launch(gma_cast_kernel<float>, static_cast<const float*>(x));
+        case SF_DT_F16: return launch(gma_cast_kernel<__half>, static_cast<const __half*>(x));
+        case SF_DT_BF16: return launch(gma_cast_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(x));
+        default: set_error("gma_cast: unsupported dtype %d", x_dtype); return SF_ERR_INVALID;
     }
 }
 

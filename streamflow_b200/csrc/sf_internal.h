@@ -168,8 +168,7 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
 struct GmaProjParams {
     const void* x;        // [P, C, N]
     int x_dtype;
-    const float* w;       // [O, C] rows o0 .. o0+O-1 used (fp32 path)
-    const __half* w16;    // [O, C] fp16 weights (gma_proj_v_kernel)
+    const float* w;       // [O, C] rows o0 .. o0+O-1 used
     int P, C, N, O;
     float scale;          // multiplies the result (q gets d^-1/2)
     __half* out;          // token-major: [P, Nrows, ldo] (ldo >= O) or channel-major: [P, O, ldn]
@@ -186,14 +185,12 @@ struct GmaProjParams {
     // optional: clear per-token accumulators of the following stats passes ([P, N] each) instead of two memsets
     unsigned* zero_u32;
     unsigned long long* zero_u64;
-    // optional fused side job (v projection): rscale[p, n] = gamma / rowsum[p, n] for the aggregate epilogue,
-    // so that no later kernel has thousands of warps reading the single gamma word
-    const float* rowsum;
-    const float* gamma;
-    float* rscale;
 };
 int launch_gma_proj(const GmaProjParams& p, cudaStream_t s);
-int launch_gma_proj_v(const GmaProjParams& p, cudaStream_t s);
+// Per-iteration operand preparation of the aggregate: x [P, C, N] (any float dtype) -> x16 [P, C, Npad] fp16 (K-major
+// over keys = NCHW, pad columns zero) and w_v [d, C] (fp32 or fp16) -> w16 [d, C] fp16.
+int launch_gma_cast(const void* x, int x_dtype, __half* x16, int64_t rows, int64_t N, int64_t Npad, const void* w,
+                    int w_dtype, __half* w16, int64_t w_elems, cudaStream_t s);
 
 struct GmaStatsParams {
     int P, N, Npad, Kp;
@@ -214,14 +211,16 @@ int launch_gma_rowsum_finish(const unsigned long long* fx, float* rowsum, long l
 struct GmaAggParams {
     int P, N, Npad, C;          // C == d == 128
     int k_blocks;               // Npad / 64
-    const float* rscale;        // [P, N] gamma / rowsum (written by the v projection)
+    const float* rowsum;        // [P, N] softmax denominators (sum of the stored numerators)
+    const float* gamma;         // device scalar
     const void* fmap;           // [P, C, N]
     int fmap_dtype;
     float* out;                 // [P, C, N]
     const __half* e_ptr;        // tile-major E (swizzled 16 KB blocks) and its per-map stride in elements
     long long e_map_stride;
 };
-int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_v, int num_sms, cudaStream_t s);
+int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_w, int num_sms,
+                         cudaStream_t s);
 int launch_gma_identity(float* dst, int d, cudaStream_t s);      // dst[d, d] <- I
 
 int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,

@@ -34,3 +34,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _inference_only():
+    """The B200 operators are inference-only and refuse to run where autograd would expect a graph (parameters that
+    require grad with grad mode on); the reference drives them under torch.no_grad() (evaluate_mf.py:468).  Tests
+    that check the refusal itself re-enable grad locally."""
+    import torch
+    with torch.no_grad():
+        yield

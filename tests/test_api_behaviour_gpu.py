@@ -27,20 +27,22 @@ def test_autograd_is_refused_not_silently_dropped():
     att, agg = _mods()
     x = torch.randn(1, 128, 16, 24, device="cuda")
     f = torch.randn(1, 32, 16, 24, device="cuda")
-    with pytest.raises(sfb.StreamCorrError, match="inference-only"):
-        att(x)                                       # parameters require grad and autograd is on
-    with pytest.raises(sfb.StreamCorrError, match="inference-only"):
-        sfb.CorrBlock(f.clone().requires_grad_(), f)
+    with torch.enable_grad():
+        with pytest.raises(sfb.StreamCorrError, match="inference-only"):
+            att(x)                                   # parameters require grad and autograd is on
+        with pytest.raises(sfb.StreamCorrError, match="inference-only"):
+            sfb.CorrBlock(f.clone().requires_grad_(), f)
     with torch.no_grad():
         h = att(x)
         blk = sfb.CorrBlock(f.clone().requires_grad_(), f)
         out = agg(h, x)
     assert not out.requires_grad and blk(sfb.coords_grid(1, 16, 24, device="cuda").contiguous()).shape == (1, 324, 16, 24)
-    with pytest.raises(sfb.StreamCorrError, match="inference-only"):
-        agg(h, x)
-    for prm in list(att.parameters()) + list(agg.parameters()):
-        prm.requires_grad_(False)
-    assert agg(att(x), x).shape == x.shape           # frozen parameters: fine with autograd enabled
+    with torch.enable_grad():
+        with pytest.raises(sfb.StreamCorrError, match="inference-only"):
+            agg(h, x)
+        for prm in list(att.parameters()) + list(agg.parameters()):
+            prm.requires_grad_(False)
+        assert agg(att(x), x).shape == x.shape       # frozen parameters: fine with autograd enabled
 
 
 def test_inference_mode_both_conventions():
