@@ -34,6 +34,8 @@
 // iterations for the same E bytes) and was the tail of the whole kernel (98 us) until the split became per-map.
 //
 // warps: 0 = E producer (bulk copies), 1 = TMEM alloc + MMA issuer, 2 = W_v + X producer (TMA), 3-10 = epilogue.
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -51,7 +53,7 @@ constexpr int kMaxEStages = 12, kVStages = 3;
 constexpr int kVBytes = kCh * BK * 2;                       // 16 KB: one key block of X (128 channels x 64 keys)
 constexpr int kWBytes = 2 * kVBytes;                        // 32 KB: W_v [c][c'] fp16 as two 64-wide k-blocks
 constexpr int kSmemBytes = 227 * 1024;                      // everything the SM has
-constexpr int kBarBytes = 512;
+constexpr int kBarBytes = 2048;                            // barriers + the 1 / rowsum row of the current segment
 constexpr int kRing = (kSmemBytes - 1024 /*align slack*/ - kBarBytes) / 1024 * 1024;
 constexpr int kTmemCols = 512;                              // 2 accumulators x 256 columns
 constexpr int kEpiWarps = 8;
@@ -67,6 +69,7 @@ struct GmaAggArgs {
     int stage_off, stage_rows;      // staging tile of the second GEMM: 4 sub-tiles [hi|lo][k-block] of stage_rows x 128 B
     int fbuf_pitch;                 // > 0: single-segment CTAs; the fmap tile is prefetched into shared memory
     int fbuf_off;                   // byte offset of that tile inside the ring area
+    int dbg;                        // STREAMCORR_AGG_DEBUG ablation bits (measurement only; results are wrong when set)
 };
 
 struct Seg {
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     uint64_t* d2_full = w_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_full + 1);
     float* gamma_s = reinterpret_cast<float*>(tmem_slot + 1);
+    float* rinv_s = reinterpret_cast<float*>(smem + kRing + 1024);     // [256] 1 / rowsum of the current segment
 
     const GmaAggParams& p = args.p;
     // warp index through a shuffle so the compiler knows the role dispatch is warp-uniform (see gma_sm100.cu)
@@ -346,36 +350,66 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
             const float* rsum = p.rowsum + static_cast<long long>(s.pb) * p.N;
             float* out = p.out + base;
             uint8_t* fbuf = smem + args.fbuf_off;
+            // While the key loop of this segment runs (the epilogue warps have nothing else to do): 1 / rowsum of its
+            // queries into shared memory, and the lines of its fmap tile into L2, so that neither is a DRAM round trip
+            // in the un-overlapped tail.  (rinv_s was last read before the previous segment's final epi_bar_sync.)
+            if (et < s.rows) {
+                const int n = s.row0 + et;
+                rinv_s[et] = (n < p.N && !(args.dbg & 1)) ? __frcp_rn(__ldg(rsum + n)) : ((args.dbg & 1) ? 1.f : 0.f);
+            }
+            if (!(args.dbg & 8)) {
+                const int valid = min(s.rows, p.N - s.row0);
+                const int lines = (valid * static_cast<int>(sizeof(T)) + 127) / 128;      // 128-byte lines per channel row
+                const uint8_t* fm0 = reinterpret_cast<const uint8_t*>(
+                    reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(s.pb) * kCh * p.N + s.row0);
+                for (int i = et; i < kCh * lines; i += kEpiWarps * 32) {
+                    const int c = i / lines, k = i - c * lines;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fm0 + static_cast<long long>(c) * p.N * sizeof(T) + k * 128));
+                }
+            }
+            epi_bar_sync();
             mbar_wait(&tfull[acc], (local >> 1) & 1);          // every MMA of the key loop is done: the rings are idle
             tc_fence_after();
-            if (single) {
+            if (single && !(args.dbg & 4)) {
                 // the un-overlapped tail of the kernel: fetch the fmap tile into the idle ring while the second GEMM runs
                 const int valid = min(s.rows, p.N - s.row0);
                 const int cpr = valid * static_cast<int>(sizeof(T)) / 16;         // 16-byte chunks per channel row
-                const T* fm0 = reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(s.pb) * kCh * p.N + s.row0;
-                for (int i = et; i < kCh * cpr; i += kEpiWarps * 32) {
-                    const int c = i / cpr, k = i - c * cpr;
-                    cp_async16(fbuf + c * args.fbuf_pitch + k * 16,
-                               reinterpret_cast<const uint8_t*>(fm0 + static_cast<long long>(c) * p.N) + k * 16);
+                const uint8_t* fm0 = reinterpret_cast<const uint8_t*>(
+                    reinterpret_cast<const T*>(p.fmap) + static_cast<long long>(s.pb) * kCh * p.N + s.row0);
+                const long long row_bytes = static_cast<long long>(p.N) * sizeof(T);
+                // chunk i = et, et + 256, ... of the [128 channels][cpr] tile, (c, k) advanced without divisions
+                const int dc = (kEpiWarps * 32) / cpr, dk = (kEpiWarps * 32) - dc * cpr;
+                int c = et / cpr, k = et - c * cpr;
+                while (c < kCh) {
+                    cp_async16(fbuf + c * args.fbuf_pitch + k * 16, fm0 + c * row_bytes + k * 16);
+                    c += dc;
+                    k += dk;
+                    if (k >= cpr) {
+                        k -= cpr;
+                        ++c;
+                    }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
 #pragma unroll 1
-            for (int q0 = 0; q0 < s.rows; q0 += SR) {          // ---- second GEMM, `SR` queries per pass
+            for (int q0 = 0; q0 < s.rows && !(args.dbg & 2); q0 += SR) {      // ---- second GEMM, `SR` queries per pass
                 const int w = min(SR, s.rows - q0);
 #pragma unroll 1
                 for (int cc = sub; cc < w / 16; cc += 2) {
                     uint32_t v[16];
                     tmem_ld_32x16(t_acc + q0 + cc * 16, v);
                     float ri[16];
-                    const int n0 = s.row0 + q0 + cc * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) ri[j] = (n0 + j < p.N) ? __frcp_rn(__ldg(rsum + n0 + j)) : 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rinv_s + q0 + cc * 16 + 4 * j);
+                        ri[4 * j] = r4.x; ri[4 * j + 1] = r4.y; ri[4 * j + 2] = r4.z; ri[4 * j + 3] = r4.w;
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float y = (n0 + j < p.N) ? __uint_as_float(v[j]) * ri[j] : 0.f;
+                        // rows past N carry rinv = 0; their E rows may be uninitialised, so select instead of multiply
+                        const float y = (ri[j] != 0.f) ? __uint_as_float(v[j]) * ri[j] : 0.f;
                         const __half hi = __float2half_rn(y);
                         const __half lo = __float2half_rn(y - __half2float(hi));
                         const uint32_t r = static_cast<uint32_t>(cc * 16 + j);
@@ -529,10 +563,15 @@ int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const C
         }
     }
     if (!single) {      // dedicated staging tile: the epilogue of one segment overlaps the key loop of the next
-        args.stage_rows = 64;
+        args.stage_rows = 32;
         args.stage_off = args.x_off - 512 * args.stage_rows;
         e_avail = args.stage_off;
     }
+    static const int dbg = [] {
+        const char* e = getenv("STREAMCORR_AGG_DEBUG");
+        return e ? atoi(e) : 0;
+    }();
+    args.dbg = dbg;
     args.e_stages = std::min(kMaxEStages, e_avail / args.e_stage_bytes);
     SF_REQUIRE(args.e_stages >= 2, "gma_aggregate: internal error, E ring of %d stages", args.e_stages);
     switch (p.fmap_dtype) {

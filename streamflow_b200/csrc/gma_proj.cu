@@ -250,30 +250,35 @@ __global__ void __launch_bounds__(256) gma_cast_kernel(const T* __restrict__ x, 
         }
         return;
     }
+    // a block covers 4096 columns of one row: thread t takes the 8-element groups t, t + 256 (coalesced 16-byte stores)
     const long long row = b / blocks_per_row;
-    const int n0 = (static_cast<int>(b - row * blocks_per_row) * 256 + threadIdx.x) * 8;
-    if (n0 >= Npad) return;
+    const int c0 = static_cast<int>(b - row * blocks_per_row) * 4096 + threadIdx.x * 8;
     const T* src = x + row * N;
-    float v[8];
-    bool done = false;
-    if constexpr (sizeof(T) == 4) {
-        if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    float v[2][8];
+    const bool vec = sizeof(T) == 4 && (N & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int n0 = c0 + g * 2048;
+        if (vec) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 a = (n0 < N) ? __ldcs(reinterpret_cast<const float4*>(src + n0)) : z;
-            const float4 c = (n0 + 4 < N) ? __ldcs(reinterpret_cast<const float4*>(src + n0 + 4)) : z;
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-            done = true;
+            const float4 a = (n0 < N) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + n0) : z;
+            const float4 c = (n0 + 4 < N) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + n0 + 4) : z;
+            v[g][0] = a.x; v[g][1] = a.y; v[g][2] = a.z; v[g][3] = a.w;
+            v[g][4] = c.x; v[g][5] = c.y; v[g][6] = c.z; v[g][7] = c.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[g][e] = (n0 + e < N) ? load_as_float<T>(src + n0 + e) : 0.f;
         }
     }
-    if (!done) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (n0 + e < N) ? load_as_float<T>(src + n0 + e) : 0.f;
+    for (int g = 0; g < 2; ++g) {
+        const int n0 = c0 + g * 2048;
+        if (n0 >= Npad) continue;
+        alignas(16) __half2 h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[g][2 * e], v[g][2 * e + 1]);
+        *reinterpret_cast<uint4*>(x16 + row * Npad + n0) = *reinterpret_cast<const uint4*>(h);
     }
-    alignas(16) __half2 h[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-    *reinterpret_cast<uint4*>(x16 + row * Npad + n0) = *reinterpret_cast<const uint4*>(h);
 }
 
 }  // namespace
@@ -309,7 +314,7 @@ int launch_gma_cast(const void* x, int x_dtype, __half* x16, int64_t rows, int64
     SF_REQUIRE(Npad % 8 == 0 && w_elems % 8 == 0, "gma_cast: Npad and the weight count must be multiples of 8");
     SF_REQUIRE((reinterpret_cast<uintptr_t>(x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w16) & 15) == 0,
                "gma_cast: outputs must be 16-byte aligned");
-    const int bpr = static_cast<int>((Npad + 2047) / 2048);
+    const int bpr = static_cast<int>((Npad + 4095) / 4096);
     const long long x_blocks = rows * bpr;
     const long long w_blocks = (w_elems + 2047) / 2048;
     SF_REQUIRE(x_blocks + w_blocks < (1ll << 31), "gma_cast: shape too large");

@@ -79,12 +79,59 @@ def test_unmodified_reference_model_epe(hw, mixed):
     print(f"[{H}x{W} amp={mixed}] worst mean EPE {worst:.5f} px, {launched} libstreamcorr launches")
 
 
-def test_gma_is_live_in_the_reference_model():
-    """gamma != 0 and the re-randomised temporal block: zeroing gamma changes the flow, so the EPE test covers GMA."""
+class _Tap:
+    """Records what the unmodified caller hands to / gets from the hot-path operators at the first refinement
+    iteration: the `corrs` argument of the update block (core/models/streamflow.py:132,136) and the input / output of
+    `update_block.aggregator` (core/update.py:769)."""
+
+    def __init__(self, model):
+        self.corrs = self.agg_in = self.agg_out = None
+        self.handles = [
+            model.update_block.register_forward_pre_hook(self._pre),
+            model.update_block.aggregator.register_forward_hook(self._agg),
+        ]
+
+    def _pre(self, mod, args):
+        if self.corrs is None:
+            self.corrs = args[2].detach().float().clone()
+            self.meta = (args[2].dtype, args[2].is_contiguous(), args[1].dtype, args[1].is_contiguous())
+
+    def _agg(self, mod, args, out):
+        if self.agg_out is None:
+            self.agg_in = args[-1].detach().float().clone()
+            self.agg_meta = (args[-1].dtype, args[-1].is_contiguous())
+            self.agg_out = out.detach().float().clone()
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+
+def test_operators_inside_the_real_caller():
+    """Operator-level parity measured INSIDE the unmodified model, on exactly the tensors the real caller produces
+    (autocast dtypes, `rearrange`d / split views): the 324-channel lookup features of iteration 0 and the GMA
+    aggregation of iteration 0 agree with the reference operators to 1e-3 (norm-wise), and zeroing gamma changes the
+    aggregator's contribution -- so GMA is live in the end-to-end EPE test."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     ref, ours, _ = _pair(4, seed=3)
     frames = mh.synthetic_clip(4, 192, 320, seed=1)
-    a = _run(ours, frames, 4)
+    tr, to = _Tap(ref), _Tap(ours)
+    a = _run(ref, frames, 2)
+    b = _run(ours, frames, 2)
+    tr.close(), to.close()
+    rel = lambda x, y: float((x - y).norm() / y.norm())
+    e_corr = rel(to.corrs, tr.corrs)
+    # iteration 0: both models see identical coords, so the lookup features must agree to operator tolerance
+    assert e_corr < 1e-3, f"lookup features inside the model: rel err {e_corr:.3e}"
+    # the aggregator's own contribution gamma * attn . v (its input differs by the upstream 1e-4, so compare deltas)
+    d_ref, d_our = tr.agg_out - tr.agg_in, to.agg_out - to.agg_in
+    e_gma = rel(d_our, d_ref)
+    print(f"inside the real caller: corr features {e_corr:.2e}, gamma*attn*v {e_gma:.2e}; corrs {to.meta}, mf {to.agg_meta}")
+    assert float(d_ref.norm()) > 1e-2 * float(tr.agg_in.norm()), "GMA contributes nothing: the test would be vacuous"
+    assert e_gma < 3e-3, f"GMA aggregation inside the model: rel err {e_gma:.3e}"   # fp16 autocast reference: ~1e-3 itself
+    assert _epe(a[0], b[0]) < 0.01
     with torch.no_grad():
         ours.update_block.aggregator.gamma.zero_()
-    b = _run(ours, frames, 4)
-    assert _epe(a[0], b[0]) > 1e-3
+    c = _run(ours, frames, 2)
+    assert _epe(b[0], c[0]) > 1e-5          # and it reaches the flow
