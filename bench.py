@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- StreamFlow correlation/GMA hot path on B200: flow frames/s + kernel rooflines.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--eager] [--quick]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1], SURVEY.md 8(d) "Config 2", operator-level synthetic): one T=4 clip at
@@ -9,16 +9,30 @@ Sintel 436x1024 (padded 440x1024 -> 55x128 at 1/8, N = 7040, D = 256, 3 frame pa
 iterations.  One STEP = one pass of the hot path over one clip per rank:
     3 x CorrBlock build  +  1 x Attention  +  12 x (3-pair lookup + Aggregate)
 (core/models/streamflow.py:110,124,132 and core/update.py:769).  Clips are independent, so ranks shard clips
-with no data-path collective (weak scaling); the only collective is the timing reduction.
+with no data-path collective (weak scaling).
 
-JSON line (rank 0): value = flow fields per second over all ranks with inputs resident in HBM; e2e = the same
-through the public Python/C-ABI call path with pinned HOST buffers (H2D of every input and D2H of the results
-inside the timed region); roofline = dominant kernel (GMA aggregate, HBM-bound E stream); kernels = the same for
-lookup / corr GEMM.  Kernel durations are measured twice with CUDA events: `us_per_launch` = the kernel launched
-back-to-back inside one CUDA graph (12 launches with the step's own inputs; an event pair between two kernels costs
-~4 us of launch serialisation, 20 % of a 20 us kernel), `us_per_launch_event_pairs_in_step` = one event pair around
-every launch inside the eager step (upper bound);
-cpu_baseline = the torch-CPU port of the reference path on this host's cores.
+JSON line (rank 0)
+  value      flow fields per second over all ranks, hot path, inputs resident in HBM.  Default launch mode: the
+             public-API calls of one clip captured once in a CUDA graph (streamflow_b200.GraphedCall) and replayed;
+             `eager_ms_per_step` is the same calls issued eagerly (--eager makes that the headline).
+  e2e        frames in -> flows out: the UNMODIFIED reference model (oracle/_ref: SKFlow_MF8 + SKUpdateBlock_TAM_v3 +
+             Twins_CSC) running on the B200 operators through streamflow_b200.install(); every step uploads the 4
+             uint8 frames from pinned host memory and downloads the 3 full-resolution flows.  Falls back to the
+             hot-path call chain with host buffers when the reference snapshot is absent (`e2e.workload` says which).
+  parity     the LAST timed step's lookup features and GMA result compared with the reference op sequence
+             (oracle/torch_port, fp32, TF32 off) on the same GPU; the run fails above 1e-3.
+  roofline   dominant kernel (GMA aggregate, HBM-bound E stream); kernels.* = the same for lookup / corr GEMM.
+             `us_per_launch` = the kernel launched back-to-back inside one CUDA graph, CUDA events around replays;
+             `us_per_launch_event_pairs_in_step` = one event pair per launch inside the eager step (upper bound).
+             `traffic` = dram bytes per launch read from the committed ncu summary (profiles/ncu_dram_bytes.json).
+  torch_gpu_baseline   the reference's own torch ops for the hot path on the SAME B200 (TF32 off = its default, and on).
+  full_model           whole-forward frames/s of the unmodified reference model on its own operators vs on the B200
+                       operators (same GPU, same weights), hot-path share of each.
+  configs              KITTI- and Spring-shaped hot-path throughput (BASELINE.json configs[2], [3]), 1 GPU.
+  streaming, kitti_x8  BASELINE.json configs[4] and [2] across the N ranks with the NCCL flow gather inside the timed
+                       region (64 frames -> 21 windows -> 63 flows; 8 KITTI clips sharded 8/N per GPU, strong scaling).
+  cpu_baseline         the reference's own CorrBlock / Attention / Aggregate (oracle/_ref, `kind: "reference"`; the
+                       torch port if the snapshot is absent) on this host's cores.
 """
 from __future__ import annotations
 
@@ -30,16 +44,20 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H8, W8, D, T, ITERS, CDIM = 55, 128, 256, 4, 12, 128
-N = H8 * W8
+D, T, ITERS, CDIM = 256, 4, 12, 128
 PAIRS = T - 1
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-# (profiles/r1c_ncu_full_summary.md); static because bench.py must not run under a profiler
-NCU_DRAM_BYTES = {"gma_aggregate": 317.3e6, "corr_lookup": 57.4e6, "corr_gemm": 222.6e6}
+SHAPES = {  # name -> (H, W of the frames, h, w at 1/8 after InputPadder)
+    "sintel_436x1024": (436, 1024, 55, 128),
+    "kitti_376x1248": (376, 1248, 47, 156),
+    "spring_1080x1920": (1080, 1920, 135, 240),
+}
+H8, W8 = SHAPES["sintel_436x1024"][2:]
+N = H8 * W8
 METRIC = "flow frames/s (Sintel 436x1024, T=4, 12 iters); corr-lookup HBM GB/s"
 WORKLOAD = "sintel_436x1024_T4_12iters_hotpath"
 
@@ -54,21 +72,46 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
-def make_inputs(seed: int):
-    """Synthetic clip, identical on every arm (torch CPU generator)."""
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, written by scripts/ncu_summary.py --json from the
+    committed `ncu --set full` capture (bench.py itself must not run under a profiler)."""
+    path = os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")
+    if not os.path.exists(path):
+        return {}, None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get("kernels", {}), d.get("source")
+
+
+def make_inputs(seed: int, h8: int = H8, w8: int = W8, pairs: int = PAIRS, clips: int = 1):
+    """Synthetic operator inputs of one clip (or `clips` clips batched), identical on every arm (torch CPU generator)."""
     import torch
     g = torch.Generator().manual_seed(seed)
+    P = pairs * clips
     # fnet output under mixed precision: fp16 values upcast to fp32, channels-last storage (streamflow.py:107)
-    fm = torch.randn(1, T, H8, W8, D, generator=g).half().float()
-    inps = torch.relu(torch.randn(PAIRS, CDIM, H8, W8, generator=g))
-    mfs = torch.randn(PAIRS, CDIM, H8, W8, generator=g)
-    ys, xs = torch.meshgrid(torch.arange(H8), torch.arange(W8), indexing="ij")
+    fm = torch.randn(clips, pairs + 1, h8, w8, D, generator=g).half().float()
+    inps = torch.relu(torch.randn(P, CDIM, h8, w8, generator=g))
+    mfs = torch.randn(P, CDIM, h8, w8, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(h8), torch.arange(w8), indexing="ij")
     grid = torch.stack((xs, ys), 0).float()[None, None]                       # [1,1,2,h,w]
-    walk = torch.cumsum(torch.randn(ITERS, PAIRS, 1, 2, H8, W8, generator=g) * 5.0 / ITERS ** 0.5, 0)
-    coords = (grid + walk).contiguous()                                       # [iters, pairs, 1, 2, h, w]
+    walk = torch.cumsum(torch.randn(ITERS, pairs, clips, 2, h8, w8, generator=g) * 5.0 / ITERS ** 0.5, 0)
+    coords = (grid + walk).contiguous()                                       # [iters, pairs, clips, 2, h, w]
     w_qk = torch.randn(2 * CDIM, CDIM, generator=g) * (CDIM ** -0.5) * 2.0
     w_v = torch.randn(CDIM, CDIM, generator=g) * (CDIM ** -0.5)
     return {"fm_nhwc": fm, "inps": inps, "mfs": mfs, "coords": coords, "w_qk": w_qk, "w_v": w_v, "gamma": 0.8}
+
+
+def make_frames(n_frames: int, H: int, W: int, seed: int):
+    """uint8 frames [n, 3, H, W]: a smooth random texture translated by a few pixels per frame, so the correlation
+    volume has real structure and the flow is Sintel-sized (torch CPU generator: identical on every rank)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    mx, my = 3 * n_frames + 8, 2 * n_frames + 8
+    base = torch.rand(1, 3, (H + my) // 4 + 2, (W + mx) // 4 + 2, generator=g)
+    base = F.interpolate(base, scale_factor=4, mode="bicubic", align_corners=False)
+    base = ((base - base.min()) / (base.max() - base.min()) * 255.0).round().clamp(0, 255).to(torch.uint8)[0]
+    return torch.stack([base[:, 2 * t + 1: 2 * t + 1 + H, 3 * t + 2: 3 * t + 2 + W] for t in range(n_frames)]).contiguous()
 
 
 class ClockSampler(threading.Thread):
@@ -129,49 +172,162 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
+def _reference_l1():
+    """The reference's own hot-path operators: oracle/_ref core/corr.py + core/gma.py (`kind: "reference"`), or the
+    torch restatement oracle/torch_port.py when the snapshot did not travel (`kind: "port"`)."""
+    import torch
+    from oracle import make_ref
+    core = make_ref.ref_core_dir()
+    if core is None:
+        from oracle import torch_port as tp
+        return "port", None, tp
+    if core not in sys.path:
+        sys.path.insert(0, core)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import corr as ref_corr
+        import gma as ref_gma
+    return "reference", (ref_corr, ref_gma), None
+
+
+class _Ns:
+    pass
+
+
+def reference_hot_path_fn(inp, device="cpu", autocast=False):
+    """Closure running `iters` refinement iterations of the hot path with the reference's operators on `device`
+    (the once-per-clip part always runs); returns (feats, out)."""
+    import torch
+    kind, mods, tp = _reference_l1()
+    fmaps = inp["fm_nhwc"].to(device).permute(0, 1, 4, 2, 3)
+    coords, inps, mfs = inp["coords"].to(device), inp["inps"].to(device), inp["mfs"].to(device)
+    pairs = fmaps.shape[1] - 1
+    ac = dict(device_type="cuda" if str(device).startswith("cuda") else "cpu", dtype=torch.float16,
+              enabled=bool(autocast))
+    if kind == "reference":
+        ref_corr, ref_gma = mods
+        att = ref_gma.Attention(args=_Ns(), dim=CDIM, heads=1, max_pos_size=160, dim_head=CDIM).to(device)
+        agg = ref_gma.Aggregate(args=_Ns(), dim=CDIM, heads=1, dim_head=CDIM).to(device)
+        with torch.no_grad():
+            att.to_qk.weight.copy_(inp["w_qk"].view(2 * CDIM, CDIM, 1, 1))
+            agg.to_v.weight.copy_(inp["w_v"].view(CDIM, CDIM, 1, 1))
+            agg.gamma.fill_(inp["gamma"])
+
+        @torch.no_grad()
+        def run(iters=ITERS):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                fns = [ref_corr.CorrBlock(fmaps[:, i], fmaps[:, i + 1], radius=4) for i in range(pairs)]
+                with torch.autocast(**ac):
+                    attn = att(inps)
+                feats = out = None
+                for it in range(iters):
+                    feats = torch.stack([fns[i](coords[it, i]) for i in range(pairs)], 0)
+                    with torch.autocast(**ac):
+                        out = agg(attn, mfs)
+            return feats, out
+    else:
+        w_qk, w_v = inp["w_qk"].to(device), inp["w_v"].to(device)
+
+        @torch.no_grad()
+        def run(iters=ITERS):
+            pyrs = [tp.CpuCorrPyramid(fmaps[:, i], fmaps[:, i + 1]) for i in range(pairs)]
+            with torch.autocast(**ac):
+                attn = tp.cpu_attention(inps, w_qk)
+            feats = out = None
+            for it in range(iters):
+                feats = torch.stack([pyrs[i](coords[it, i]) for i in range(pairs)], 0)
+                with torch.autocast(**ac):
+                    out = tp.cpu_aggregate(attn, mfs, w_v, inp["gamma"])
+            return feats, out
+    return kind, run
+
+
+def cpu_hot_path_sample(inp, sample_iters):
+    """One bounded CPU sample of the hot path: the once-per-clip part + `sample_iters` of the 12 iterations, the
+    iteration part scaled to 12 (iterations are identical work).  Returns seconds for the full workload."""
+    kind, run = reference_hot_path_fn(inp, "cpu")
+    t0 = time.perf_counter()
+    run(0)
+    t1 = time.perf_counter()
+    run(sample_iters)
+    t2 = time.perf_counter()
+    once = t1 - t0
+    per_iter = max((t2 - t1) - once, 0.0) / sample_iters
+    return kind, once + ITERS * per_iter
+
+
+def cpu_full_model_sample(frames_u8):
+    """One bounded CPU sample of the reference's FULL forward (oracle/_ref model on its own operators): 2 of the 12
+    iterations run, the time of one iteration (between two update-block calls) is scaled to 12."""
+    import torch
+    from oracle import ref_model as rm
+    mod = rm.load_model_module("reference")
+    st = cpu_full_model_sample.__dict__
+    if "model" not in st:
+        torch.manual_seed(0)
+        st["model"] = rm.randomise(rm.build_model(mod), seed=1).eval()
+    model = st["model"]
+    stamps = []
+    h = model.update_block.register_forward_pre_hook(lambda m, a: stamps.append(time.perf_counter()))
+    frames = [f[None].float() for f in frames_u8]
+    from streamflow_b200.flowio import InputPadder
+    padder = InputPadder(frames[0].shape)
+    try:
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            model(padder.pad_list(frames), iters=2, test_mode=True)
+            t1 = time.perf_counter()
+    finally:
+        h.remove()
+    per_iter = stamps[1] - stamps[0]
+    return (t1 - t0) + (ITERS - 2) * per_iter
+
+
 def run_reference(args):
     import torch
-    from oracle import torch_port as tp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    torch.set_grad_enabled(False)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inp = make_inputs(0)
-    fmaps = inp["fm_nhwc"].permute(0, 1, 4, 2, 3)
-    coords = inp["coords"]
-
-    # Bounded sample: a full step is 0.4-2 s of CPU work.  For long runs (K > 30) each step runs the once-per-clip
-    # part (3 builds + attention) and only `sample_iters` of the 12 refinement iterations; the iteration part is
-    # scaled by 12 / sample_iters (iterations are identical work), so the value stays "flows/s for the full workload".
+    # bounded sample: a full step is 0.4-2 s of CPU work; long runs sample 2 of the 12 iterations per step
     sample_iters = ITERS if args.steps <= 30 else 2
-
-    @torch.no_grad()
-    def step():
-        t0 = time.perf_counter()
-        pyrs = [tp.CpuCorrPyramid(fmaps[:, i], fmaps[:, i + 1]) for i in range(PAIRS)]
-        attn = tp.cpu_attention(inp["inps"], inp["w_qk"])
-        t1 = time.perf_counter()
-        for it in range(sample_iters):
-            torch.stack([pyrs[i](coords[it, i]) for i in range(PAIRS)], 0)
-            tp.cpu_aggregate(attn, inp["mfs"], inp["w_v"], inp["gamma"])
-        t2 = time.perf_counter()
-        return (t1 - t0) + (t2 - t1) * (ITERS / sample_iters)
-
+    kind = "port"
     for _ in range(args.warmup):
-        step()
-    dt = sum(step() for _ in range(args.steps)) / args.steps
+        kind, _ = cpu_hot_path_sample(inp, min(sample_iters, 2))
+    dts = []
+    for _ in range(args.steps):
+        kind, dt = cpu_hot_path_sample(inp, sample_iters)
+        dts.append(dt)
+    dt = sum(dts) / len(dts)
     val = PAIRS / dt
+    sample = (f"{args.steps} steps of 1 clip: 3 builds + attention + {sample_iters} of 12 iterations (3 lookups + "
+              f"aggregate), iteration time scaled x{ITERS / sample_iters:g}; fp32 torch CPU, {cores} threads")
+    e2e = {"value": val, "unit": "flow frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "workload": WORKLOAD}
+    from oracle import ref_model as rm
+    if rm.available() and not args.quick:
+        # the reference's whole forward on CPU, the counterpart of our arm's frames-in -> flows-out `e2e`
+        frames = make_frames(T, 436, 1024, 0)
+        n = max(1, min(args.steps, 3))
+        cpu_full_model_sample(frames)                                  # warm-up (weights, thread pools)
+        full = sum(cpu_full_model_sample(frames) for _ in range(n)) / n
+        e2e = {"value": PAIRS / full, "unit": "flow frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "ms_per_step": full * 1e3, "workload": "sintel_436x1024_T4_12iters_full_model",
+               "sample": f"{n} forwards of the unmodified reference model (oracle/_ref) on CPU with 2 of 12 iterations "
+                         "run; one iteration's time (between two update-block calls) scaled to 12"}
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "flow frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (torch CPU port of "
-                   "core/corr.py + core/gma.py; the reference checkout cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": val, "unit": "flow frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of 1 clip: 3 builds + attention + {sample_iters} of 12 iterations "
-                                   f"(3 lookups + aggregate), iteration time scaled x{ITERS / sample_iters:g}"},
-        "e2e": {"value": val, "unit": "flow frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "note": "the reference's own CPU implementation of the path on the host cores"
+                   if kind == "reference" else "torch CPU port of core/corr.py + core/gma.py (oracle/_ref absent)"},
+        "cpu_baseline": {"value": val, "unit": "flow frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": e2e,
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -179,11 +335,106 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- our arm (GPU)
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+class HotPath:
+    """The hot path of one clip (or a batch of clips) through the public API -- what core/models/streamflow.py drives."""
+
+    def __init__(self, sfb, dev, host):
+        import torch
+        self.sfb, self.dev = sfb, dev
+        self.att = sfb.Attention(args=_Ns(), dim=CDIM, heads=1, max_pos_size=160, dim_head=CDIM).to(dev)
+        self.agg = sfb.Aggregate(args=_Ns(), dim=CDIM, heads=1, dim_head=CDIM).to(dev)
+        with torch.no_grad():
+            self.att.to_qk.weight.copy_(host["w_qk"].view(2 * CDIM, CDIM, 1, 1))
+            self.agg.to_v.weight.copy_(host["w_v"].view(CDIM, CDIM, 1, 1))
+            self.agg.gamma.fill_(host["gamma"])
+
+    def __call__(self, t, iters=ITERS):
+        fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)                         # [B, T, D, h, w] channels-last views
+        pairs = fmaps.shape[1] - 1
+        group = self.sfb.CorrGroup.from_fmaps(fmaps, radius=4)              # the T-1 pyramids, one batched build
+        handle = self.att(t["inps"])
+        feats = out = None
+        for it in range(iters):
+            feats = group([t["coords"][it, i] for i in range(pairs)])
+            out = self.agg(handle, t["mfs"])
+        return feats, out
+
+
+def _time_events(fn, steps, warmup, barrier, extra_streams=()):
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    for st in extra_streams:
+        torch.cuda.current_stream().wait_stream(st)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def load_full_models(dev):
+    """(reference model on its own operators, the same model on the B200 operators), identical weights; None when the
+    reference snapshot (oracle/_ref) is absent."""
+    import torch
+    from oracle import ref_model as rm
+    if not rm.available():
+        return None
+    import streamflow_b200 as sfb
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_mod, our_mod = rm.load_model_module("reference"), rm.load_model_module("b200")
+        torch.manual_seed(0)
+        ref = rm.randomise(rm.build_model(ref_mod), seed=1).to(dev).eval()
+        ours = rm.build_model(our_mod).to(dev).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    if ours.update_block.aggregator.__class__ is not sfb.Aggregate or our_mod.CorrBlock is not sfb.CorrBlock:
+        raise SystemExit("bench.py: install() did not bind the B200 operators into the reference model")
+    return ref, ours
+
+
+class FullModelRunner:
+    """frames (uint8, pinned host) -> flows (fp32, pinned host) through a StreamFlow model on `dev`."""
+
+    def __init__(self, model, dev, H, W, T=4, iters=ITERS):
+        import torch
+        from streamflow_b200.flowio import InputPadder
+        self.model, self.dev, self.iters, self.T = model, dev, iters, T
+        self.padder = InputPadder((H, W))
+        self.dev_frames = torch.empty((T, 3, H, W), dtype=torch.uint8, device=dev)
+        self.host_flows = torch.empty((T - 1, 2, H, W), dtype=torch.float32).pin_memory()
+        self.h2d = T * 3 * H * W
+        self.d2h = (T - 1) * 2 * H * W * 4
+
+    def flows_on_device(self, frames_u8):
+        """frames_u8: [T, 3, H, W] uint8 (pinned host or device) -> [T-1, 2, H, W] fp32 on the device."""
+        import torch
+        self.dev_frames.copy_(frames_u8, non_blocking=True)
+        frames = [f[None].float() for f in self.dev_frames]
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = self.model(self.padder.pad_list(frames), iters=self.iters, test_mode=True)
+        return torch.cat([self.padder.unpad(o) for o in out], 0)
+
+    def __call__(self, frames_u8):
+        flows = self.flows_on_device(frames_u8)
+        self.host_flows.copy_(flows, non_blocking=True)
+        return flows
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import streamflow_b200 as sfb
     from streamflow_b200 import _lib
+    from streamflow_b200 import dist as sfd
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,145 +443,123 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     torch.set_grad_enabled(False)                 # inference-only operators (the reference evaluates under no_grad)
+    torch.backends.cuda.matmul.allow_tf32 = False  # the reference never enables TF32
+    torch.backends.cudnn.allow_tf32 = False
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     L = sfb.lib()
     peaks = load_peaks()
-
-    class _A:
-        pass
-
-    host = make_inputs(rank)                      # each rank owns a different clip (weak scaling)
-    att = sfb.Attention(args=_A(), dim=CDIM, heads=1, max_pos_size=160, dim_head=CDIM).to(dev)
-    agg = sfb.Aggregate(args=_A(), dim=CDIM, heads=1, dim_head=CDIM).to(dev)
-    with torch.no_grad():
-        att.to_qk.weight.copy_(host["w_qk"].view(2 * CDIM, CDIM, 1, 1))
-        agg.to_v.weight.copy_(host["w_v"].view(CDIM, CDIM, 1, 1))
-        agg.gamma.fill_(host["gamma"])
-
-    pinned = {k: host[k].pin_memory() for k in ("fm_nhwc", "inps", "mfs", "coords")}
-    resident = {k: v.to(dev) for k, v in pinned.items()}
-    out_feats_host = torch.empty((PAIRS, 324, H8, W8), dtype=torch.float32).pin_memory()
-    out_agg_host = torch.empty((PAIRS, CDIM, H8, W8), dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
-    d2h = out_feats_host.numel() * 4 + out_agg_host.numel() * 4
-
-    def hot_path(t):
-        """The hot path for one clip through the public API (what core/models/streamflow.py drives)."""
-        fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)                         # [1, T, D, h, w] channels-last views
-        group = sfb.CorrGroup.from_fmaps(fmaps, radius=4)                   # the T-1 pyramids, one batched build
-        handle = att(t["inps"])
-        feats = out = None
-        for it in range(ITERS):
-            feats = group([t["coords"][it, i] for i in range(PAIRS)])
-            out = agg(handle, t["mfs"])
-        return feats, out
-
-    # Default: eager public-API calls.  `--graph` captures the whole clip once (streamflow_b200.GraphedCall) and
-    # replays it: same kernels, ~45 launches less CPU latency per clip.  Measured: 1.45 vs 1.53 ms in a 10-step
-    # burst, no difference over 200 sustained steps (the board sits on its power cap either way).
-    use_graph = args.graph
-
-    def step_eager():
-        return hot_path(resident)
-
-    graphed_resident = sfb.GraphedCall(step_eager) if use_graph else None
-    step_resident = graphed_resident if use_graph else step_eager
-
-    # e2e: every step uploads its inputs from pinned host memory and downloads its results.  The three phases run
-    # on three streams with double-buffered device inputs / host outputs, so the upload of step i+1 and the
-    # download of step i-1 overlap the kernels of step i (PCIe is full duplex) -- a streaming deployment.
-    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in pinned.items()} for _ in range(2)]
-    host_out = [(torch.empty_like(out_feats_host).pin_memory(), torch.empty_like(out_agg_host).pin_memory())
-                for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]         # upload i done
-    ev_free = [torch.cuda.Event() for _ in range(2)]       # compute that read dev_in[i] done
-    ev_done = [torch.cuda.Event() for _ in range(2)]       # results of slot i ready on the compute stream
-    ev_out = [torch.cuda.Event() for _ in range(2)]        # download of slot i done (host buffer reusable)
-    e2e_state = {"i": 0}
-    graphed_slot = [sfb.GraphedCall(lambda s=s_: hot_path(dev_in[s])) for s_ in range(2)] if use_graph else None
-
-    def step_e2e():
-        i = e2e_state["i"]
-        slot = i & 1
-        e2e_state["i"] = i + 1
-        cur = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(s_in):
-            if i >= 2:
-                s_in.wait_event(ev_free[slot])
-            for k, v in pinned.items():
-                dev_in[slot][k].copy_(v, non_blocking=True)
-            ev_in[slot].record(s_in)
-        cur.wait_event(ev_in[slot])
-        if use_graph:
-            if i >= 2:
-                cur.wait_event(ev_out[slot])               # the graph's static outputs of this slot were downloaded
-            feats, out = graphed_slot[slot]()
-        else:
-            feats, out = hot_path(dev_in[slot])
-        ev_free[slot].record(cur)
-        ev_done[slot].record(cur)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_done[slot])
-            if i >= 2:
-                ev_out[slot].synchronize()                 # host buffer of this slot was drained two steps ago
-            host_out[slot][0].copy_(feats, non_blocking=True)
-            host_out[slot][1].copy_(out, non_blocking=True)
-            feats.record_stream(s_out)
-            out.record_stream(s_out)
-            ev_out[slot].record(s_out)
+    traffic, traffic_src = load_ncu_traffic()
 
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()                           # all streams, incl. the e2e copy streams
+        torch.cuda.synchronize()
 
-    def time_steps(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        for st in (s_in, s_out):                           # the timed region ends when the last download lands
-            torch.cuda.current_stream(dev).wait_stream(st)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1) / steps
+    def max_over_ranks(ms):
         if world > 1:
             tt = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
+            return float(tt.item())
         return ms
 
-    # ---- headline: device-resident inputs
+    host = make_inputs(rank)                      # each rank owns a different clip (weak scaling)
+    hot = HotPath(sfb, dev, host)
+    resident = {k: host[k].to(dev) for k in ("fm_nhwc", "inps", "mfs", "coords")}
+
+    # ---- headline: device-resident inputs; CUDA-graph replay of the public-API calls unless --eager
+    def step_eager():
+        return hot(resident)
+
+    graphed = None if args.eager else sfb.GraphedCall(step_eager)
+    step_resident = step_eager if args.eager else graphed
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.sf_launch_count()
     if sampler:
         sampler.start()
-    ms_step = time_steps(step_resident, args.steps, args.warmup)
+    ms_step = max_over_ranks(_time_events(step_resident, args.steps, args.warmup, barrier))
     clocks = sampler.stop() if sampler else None
-    if use_graph:
-        launches = graphed_resident.launches * args.steps
-        ms_eager = time_steps(step_eager, min(args.steps, 50), 3)
-    else:
+    if args.eager:
         launches = (L.sf_launch_count() - launches0) * args.steps // (args.steps + args.warmup)
         ms_eager = ms_step
+    else:
+        launches = graphed.launches * args.steps
+        ms_eager = max_over_ranks(_time_events(step_eager, min(args.steps, 50), 3, barrier))
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region
-    ms_e2e = time_steps(step_e2e, args.steps, max(args.warmup, 3))
+    # ---- parity of what was just timed: last step's outputs vs the reference op sequence on the same GPU (fp32)
+    feats, out = step_resident()
+    torch.cuda.synchronize()
+    from oracle import torch_port as tp                                   # the checker, never the thing measured
+    fm = resident["fm_nhwc"].permute(0, 1, 4, 2, 3)
+    ref_feats = torch.stack([tp.CpuCorrPyramid(fm[:, i], fm[:, i + 1])(resident["coords"][ITERS - 1, i])
+                             for i in range(PAIRS)], 0).reshape(feats.shape)
+    w_qk, w_v = host["w_qk"].to(dev), host["w_v"].to(dev)
+    ref_out = tp.cpu_aggregate(tp.cpu_attention(resident["inps"], w_qk), resident["mfs"], w_v, host["gamma"])
+    parity = {"corr_rel": _rel(feats, ref_feats), "gma_rel": _rel(out - resident["mfs"], ref_out - resident["mfs"]),
+              "bound": 1e-3, "checker": "oracle/torch_port op sequence on the same GPU, fp32, TF32 off, same inputs as "
+                                        "the timed step (last iteration)"}
+    del ref_feats, ref_out
+    ok = torch.tensor([float(parity["corr_rel"] < 1e-3 and parity["gma_rel"] < 1e-3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) < 1.0:
+        raise SystemExit(f"bench.py: parity check failed on rank {rank}: {parity}")
+    torch.cuda.empty_cache()
 
-    # ---- per-kernel event timing inside a timed region of `steps` steps
-    def kernel_time(which):
-        """Mean duration (us) of kernel `which`, one CUDA-event pair per launch, over timed steps."""
-        durs = [_step_with_kernel_events(which) for _ in range(max(3, min(args.steps, 5)))]
-        flat = [d for ds in durs[1:] for d in ds]
-        return sum(flat) / len(flat), len(flat)
+    # ---- e2e
+    models = None if args.quick else load_full_models(dev)
+    e2e, full_model = None, None
+    if models is not None:
+        ref_model, our_model = models
+        Hs, Ws = SHAPES["sintel_436x1024"][:2]
+        frames_host = make_frames(T, Hs, Ws, 100 + rank).pin_memory()
+        runner = FullModelRunner(our_model, dev, Hs, Ws)
+        k_e2e = max(3, min(args.steps, 10))
+        ms_e2e = max_over_ranks(_time_events(lambda: runner(frames_host), k_e2e, 3, barrier))
+        e2e = {"value": world * PAIRS / (ms_e2e / 1e3), "unit": "flow frames/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": runner.h2d, "d2h_bytes_per_step": runner.d2h, "steps": k_e2e,
+               "workload": "sintel_436x1024_T4_12iters_full_model",
+               "note": "uint8 frames from pinned host memory -> unmodified reference model (oracle/_ref SKFlow_MF8 / "
+                       "SKUpdateBlock_TAM_v3 / Twins_CSC, eager PyTorch, fp16 autocast) on the B200 operators via "
+                       "streamflow_b200.install() -> full-resolution flows to pinned host memory"}
+        if rank == 0 and world == 1:
+            ref_runner = FullModelRunner(ref_model, dev, Hs, Ws)
+            ms_ref = _time_events(lambda: ref_runner(frames_host), k_e2e, 3, barrier)
+            fo = runner.flows_on_device(frames_host)
+            fr = ref_runner.flows_on_device(frames_host)
+            epe = torch.sqrt(((fo - fr) ** 2).sum(1)).mean(dim=(1, 2))
+            full_model = {"b200_l1_ms": ms_e2e, "reference_l1_ms": ms_ref,
+                          "b200_l1_flows_per_s": PAIRS / (ms_e2e / 1e3), "reference_l1_flows_per_s": PAIRS / (ms_ref / 1e3),
+                          "speedup": ms_ref / ms_e2e, "hot_path_share_b200": ms_eager / ms_e2e,
+                          "mean_epe_px_per_pair": [float(x) for x in epe],
+                          "flow_magnitude_px": float(torch.sqrt((fr ** 2).sum(1)).mean()),
+                          "note": "whole forward incl. H2D of frames and D2H of flows, same GPU, same random-init weights "
+                                  "(gamma ~ U(0.5,1.5), temporal block re-randomised), TF32 off; everything outside the "
+                                  "hot path is the reference's unchanged eager PyTorch code"}
+            del ref_runner, fo, fr
+    else:
+        # fallback boundary: the hot-path call chain itself with host buffers (fm uploaded as the fp16 it is)
+        pinned = {"fm_nhwc": host["fm_nhwc"].half().pin_memory(), "inps": host["inps"].pin_memory(),
+                  "mfs": host["mfs"].pin_memory(), "coords": host["coords"].pin_memory()}
+        dev_in = {k: torch.empty_like(v, device=dev) for k, v in pinned.items()}
+        host_out = [torch.empty((PAIRS, 324, H8, W8)).pin_memory(), torch.empty((PAIRS, CDIM, H8, W8)).pin_memory()]
 
+        def step_e2e():
+            for k, v in pinned.items():
+                dev_in[k].copy_(v, non_blocking=True)
+            f, o = hot(dev_in)
+            host_out[0].copy_(f, non_blocking=True)
+            host_out[1].copy_(o, non_blocking=True)
+
+        ms_e2e = max_over_ranks(_time_events(step_e2e, args.steps, max(args.warmup, 3), barrier))
+        e2e = {"value": world * PAIRS / (ms_e2e / 1e3), "unit": "flow frames/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()),
+               "d2h_bytes_per_step": sum(v.numel() * 4 for v in host_out), "workload": WORKLOAD,
+               "note": "oracle/_ref absent: hot-path call chain with pinned host buffers"}
+
+    # ---- per-kernel timing
     def _raw_event():
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()          # forces creation of the underlying cudaEvent_t
@@ -339,12 +568,12 @@ def run_ours(args):
     def _step_with_kernel_events(which):
         t = resident
         fmaps = t["fm_nhwc"].permute(0, 1, 4, 2, 3)
-        pairs = []
+        pairs_ev = []
 
         def arm():
             a, b = _raw_event(), _raw_event()
             L.sf_profile_kernel(which, a.cuda_event, b.cuda_event)
-            pairs.append((a, b))
+            pairs_ev.append((a, b))
 
         def disarm():
             L.sf_profile_kernel(0, None, None)
@@ -355,7 +584,7 @@ def run_ours(args):
         disarm()
         if which == _lib.KERNEL_GMA_STATS:
             arm()
-        handle = att(t["inps"])
+        handle = hot.att(t["inps"])
         disarm()
         for it in range(ITERS):
             if which == _lib.KERNEL_LOOKUP:
@@ -364,10 +593,15 @@ def run_ours(args):
             disarm()
             if which in (_lib.KERNEL_GMA_AGGREGATE, _lib.KERNEL_GMA_PROJ):
                 arm()
-            agg(handle, t["mfs"])
+            hot.agg(handle, t["mfs"])
             disarm()
         torch.cuda.synchronize()
-        return [a.elapsed_time(b) * 1e3 for a, b in pairs]       # microseconds
+        return [a.elapsed_time(b) * 1e3 for a, b in pairs_ev]       # microseconds
+
+    def kernel_time(which):
+        durs = [_step_with_kernel_events(which) for _ in range(3)]
+        flat = [d for ds in durs[1:] for d in ds]
+        return sum(flat) / len(flat), len(flat)
 
     def graph_kernel_time(fn, calls, gma_mask=7, corr_mask=3, replays=5):
         """Kernel duration without event gaps: `calls` back-to-back launches captured in ONE CUDA graph with the
@@ -400,71 +634,166 @@ def run_ours(args):
     if rank == 0:
         hbm = peaks["hbm_gbs"]
         fm_views = resident["fm_nhwc"].permute(0, 1, 4, 2, 3)
-        g_blocks = [sfb.CorrBlock(fm_views[:, i], fm_views[:, i + 1], radius=4) for i in range(PAIRS)]
-        g_group = sfb.CorrGroup(g_blocks)
+        g_group = sfb.CorrGroup.from_fmaps(fm_views, radius=4)
         # two independent sets of softmax numerators, alternated, so no launch can find its own 297 MB stream
         # left over in the 126 MB L2 by the previous launch
-        g_handle = [att(resident["inps"]), att(resident["inps"])]
+        g_handle = [hot.att(resident["inps"]), hot.att(resident["inps"])]
         us_graph = {
-            "gma_aggregate": graph_kernel_time(lambda i: agg(g_handle[i & 1], resident["mfs"]), ITERS, gma_mask=2),
+            "gma_aggregate": graph_kernel_time(lambda i: hot.agg(g_handle[i & 1], resident["mfs"]), ITERS, gma_mask=2),
+            "gma_cast": graph_kernel_time(lambda i: hot.agg(g_handle[i & 1], resident["mfs"]), ITERS, gma_mask=1),
             "corr_lookup": graph_kernel_time(
                 lambda i: g_group([resident["coords"][i % ITERS, j] for j in range(PAIRS)]), ITERS),
             "corr_gemm": graph_kernel_time(lambda i: sfb.CorrGroup.from_fmaps(fm_views, radius=4), 4, corr_mask=2),
         }
-        del g_blocks, g_group, g_handle
+        del g_group, g_handle
         us, n = kernel_time(_lib.KERNEL_GMA_AGGREGATE)
         npad = L.sf_gma_npad(N)
-        # E stream + V + the fused epilogue's fmap read and result write, per launch
+        # E stream + fp16 X + the fused epilogue's fmap read and result write, per launch
         bytes_agg = PAIRS * N * npad * 2 + PAIRS * CDIM * npad * 2 + 2 * PAIRS * CDIM * N * 4
         ug = us_graph["gma_aggregate"]
         kernels["gma_aggregate"] = {"bound": "hbm", "achieved": bytes_agg / ug / 1e3, "peak": hbm, "unit": "GB/s",
                                     "frac": bytes_agg / ug / 1e3 / hbm, "us_per_launch": ug,
                                     "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
-                                    "algorithmic_bytes": bytes_agg, "traffic": NCU_DRAM_BYTES["gma_aggregate"],
-                                    "flops": 2.0 * PAIRS * N * N * CDIM}
+                                    "algorithmic_bytes": bytes_agg, "traffic": traffic.get("gma_aggregate"),
+                                    "flops": 2.0 * PAIRS * N * N * CDIM,
+                                    "tensor_frac_if_P_cached": 2.0 * PAIRS * N * N * CDIM / ug / 1e6 / peaks["bf16_tflops"]}
         us, n = kernel_time(_lib.KERNEL_LOOKUP)
         bytes_lk = 2904 * PAIRS * N
         ug = us_graph["corr_lookup"]
         kernels["corr_lookup"] = {"bound": "hbm", "achieved": bytes_lk / ug / 1e3, "peak": hbm, "unit": "GB/s",
                                   "frac": bytes_lk / ug / 1e3 / hbm, "us_per_launch": ug,
                                   "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
-                                  "algorithmic_bytes": bytes_lk, "traffic": NCU_DRAM_BYTES["corr_lookup"],
-                                  "note": "3 pairs per launch, coords random-walk; pyramid 805 MB >> L2; the 27 MB "
-                                          "of stores mostly leave L2 after the kernel (cold ncu counts 2.4 MB)"}
+                                  "algorithmic_bytes": bytes_lk, "traffic": traffic.get("corr_lookup"),
+                                  "note": "3 pairs per launch, coords random-walk; pyramid 805 MB >> L2"}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D * PAIRS                     # one launch builds the pyramids of all pairs
         us_ev, us = us, us_graph["corr_gemm"]
         tf = flops / us / 1e6
         peak_tf = peaks["bf16_tflops"]
-        out_bytes = PAIRS * 4 * N * sum((H8 >> l) * (((W8 >> l) + 3) // 4 * 4) for l in range(4))
+        out_bytes = PAIRS * 4 * N * sum(((H8 >> l) + 3) // 4 * (((W8 >> l) + 3) // 4) * 16 for l in range(4))
         kernels["corr_gemm"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                                 "frac": tf / peak_tf, "us_per_launch": us,
                                 "us_per_launch_event_pairs_in_step": us_ev, "launches_timed": n,
-                                "algorithmic_flops": flops, "store_gbs": out_bytes / us / 1e3,
-                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": PAIRS * NCU_DRAM_BYTES["corr_gemm"],
+                                "algorithmic_flops": flops, "store_bytes": out_bytes, "store_gbs": out_bytes / us / 1e3,
+                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": traffic.get("corr_gemm"),
                                 "note": "one launch = the %d pairs of the clip; fp16 operands (kind::f16), fp32 accumulate; "
-                                        "output-store bound" % PAIRS}
-
-        # the small helper kernels, for the step budget in DESIGN.md (event pair brackets the last launch of the
-        # kind inside each public call)
-        for name, kind in (("gma_proj_v", _lib.KERNEL_GMA_PROJ), ("gma_stats_pass2", _lib.KERNEL_GMA_STATS),
-                           ("corr_pack", _lib.KERNEL_CORR_PACK)):
+                                        "output-store bound: store_frac_of_hbm is the binding roofline" % PAIRS}
+        kernels["gma_cast"] = {"us_per_launch": us_graph["gma_cast"]}
+        for name, kind in (("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
             us, n = kernel_time(kind)
-            kernels[name] = {"us_per_launch": us, "launches_timed": n}
+            kernels[name] = {"us_per_launch_event_pairs_in_step": us, "launches_timed": n}
+        torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N=1 only): one full step of the torch CPU port
+    # ---- the reference's torch ops on the SAME GPU (like-for-like bar), rank 0 at N=1
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.quick:
+        torch_gpu = {}
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            kind, run = reference_hot_path_fn(host, dev, autocast=True)
+            ms = _time_events(run, 3, 2, barrier)
+            torch_gpu["tf32_on" if tf32 else "tf32_off"] = {"ms_per_step": ms, "flows_per_s": PAIRS / (ms / 1e3)}
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch_gpu["kind"] = kind
+        torch_gpu["speedup_vs_tf32_off"] = torch_gpu["tf32_off"]["ms_per_step"] / ms_eager
+        torch_gpu["note"] = ("the reference's own CorrBlock / Attention / Aggregate (fp16 autocast GMA as in the model) "
+                             "eager on this GPU, same workload as `value`; compared with our eager step")
+        del run
+        torch.cuda.empty_cache()
+
+    # ---- KITTI- and Spring-shaped hot path (BASELINE.json configs[2], [3]), rank 0 at N=1
+    configs = None
+    if rank == 0 and world == 1 and not args.quick:
+        configs = {}
+        for name in ("kitti_376x1248", "spring_1080x1920"):
+            h8, w8 = SHAPES[name][2:]
+            hi = make_inputs(7, h8, w8)
+            res = {k: hi[k].to(dev) for k in ("fm_nhwc", "inps", "mfs", "coords")}
+            gcall = sfb.GraphedCall(lambda: hot(res))
+            reps = 20 if name.startswith("kitti") else 4
+            ms = _time_events(gcall, reps, 2, barrier)
+            n_ = h8 * w8
+            configs[name] = {"ms_per_clip": ms, "flows_per_s": PAIRS / (ms / 1e3), "N": n_, "steps": reps,
+                             "pyramid_gb": PAIRS * 4 * n_ * sum(((h8 >> l) + 3) // 4 * (((w8 >> l) + 3) // 4) * 16
+                                                               for l in range(4)) / 1e9,
+                             "softmax_numerators_gb": PAIRS * L.sf_gma_e_elems(1, n_) * 2 / 1e9,
+                             "launch": "cuda_graph replay, one clip of T=4, 12 iterations, hot path"}
+            del gcall, res, hi
+            torch.cuda.empty_cache()
+
+    # ---- multi-GPU legs with the ONE collective of the design: the NCCL gather of the output flows
+    streaming = kitti_x8 = None
+    if models is not None and not args.quick:
+        our_model = models[1]
+        # config 5: 64 frames -> 21 overlapping T=4 windows -> 63 flows, windows block-partitioned over the ranks
+        Hs, Ws = SHAPES["sintel_436x1024"][:2]
+        n_frames = args.stream_frames
+        video = make_frames(n_frames, Hs, Ws, 0).pin_memory()            # identical on every rank
+        runner = FullModelRunner(our_model, dev, Hs, Ws)
+
+        def flow_fn(window):
+            return list(runner.flows_on_device(torch.stack(window)))
+
+        frames_list = list(video)
+        runner.flows_on_device(video[:T])                                  # warm-up
+        tm = {}
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flows = sfd.run_windows(frames_list, flow_fn, T=T, timings=tm)
+        host_flows = flows.cpu() if rank == 0 else None                   # rank 0 hands the sequence to the caller
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        gather_ms = tm["gather_events"][0].elapsed_time(tm["gather_events"][1]) if "gather_events" in tm else 0.0
+        gather_ms = max_over_ranks(gather_ms)
+        if tuple(flows.shape) != (n_frames - 1, 2, Hs, Ws) or not bool(torch.isfinite(flows).all()):
+            raise SystemExit(f"bench.py: streaming gather returned {tuple(flows.shape)}")
+        wpr = tm.get("windows_per_rank", [len(sfd.window_schedule(n_frames, T))])
+        streaming = {"frames": n_frames, "windows": sum(wpr), "flows": n_frames - 1, "windows_per_rank": wpr,
+                     "critical_path_windows": max(wpr), "ms_total": ms_total, "flows_per_s": (n_frames - 1) / (ms_total / 1e3),
+                     "gather_ms": gather_ms, "gather_bytes_per_rank": tm.get("gather_bytes", 0),
+                     "collective": "torch.distributed all_gather_into_tensor over NCCL (inside the timed region)" if world > 1
+                     else "none (1 rank)",
+                     "note": "demo.py:518-532 window loop; full model per window (uint8 frames H2D, flows stay on the "
+                             "device until the gather; rank 0 copies the 63 flows to the host inside the timed region)"}
+        del flows, host_flows, video, frames_list
+        # config 3: 8 KITTI-shaped clips sharded 8/N per GPU (strong scaling)
+        if world <= 8:
+            Hk, Wk = SHAPES["kitti_376x1248"][:2]
+            clips = [make_frames(T, Hk, Wk, s).pin_memory() for s in range(8)]
+            krunner = FullModelRunner(our_model, dev, Hk, Wk)
+            krunner.flows_on_device(clips[0])
+            tm = {}
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            kflows = sfd.run_clips(clips, krunner.flows_on_device, timings=tm)
+            e1.record()
+            barrier()
+            ms_total = max_over_ranks(e0.elapsed_time(e1))
+            gather_ms = tm["gather_events"][0].elapsed_time(tm["gather_events"][1]) if "gather_events" in tm else 0.0
+            if tuple(kflows.shape) != (8 * PAIRS, 2, Hk, Wk):
+                raise SystemExit(f"bench.py: KITTI gather returned {tuple(kflows.shape)}")
+            kitti_x8 = {"clips": 8, "clips_per_rank": tm.get("clips_per_rank", [8]), "ms_total": ms_total,
+                        "flows_per_s": 8 * PAIRS / (ms_total / 1e3), "gather_ms": max_over_ranks(gather_ms),
+                        "gather_bytes_per_rank": tm.get("gather_bytes", 0), "scaling": "strong"}
+            del kflows, clips
+        torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own operators on this host's cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import torch_port as tp
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        fm_cpu = host["fm_nhwc"].permute(0, 1, 4, 2, 3)
-        tp.cpu_hot_path(fm_cpu, host["coords"][:2], host["inps"], host["mfs"], host["w_qk"], host["w_v"], host["gamma"])
-        t0 = time.perf_counter()
-        tp.cpu_hot_path(fm_cpu, host["coords"], host["inps"], host["mfs"], host["w_qk"], host["w_v"], host["gamma"])
-        dt = time.perf_counter() - t0
-        cpu = {"value": PAIRS / dt, "unit": "flow frames/s", "cores": cores, "kind": "port",
-               "sample": "1 full step (1 clip: 3 builds + attention + 12 x (3 lookups + aggregate)), fp32 torch CPU"}
+        cpu_hot_path_sample(host, 1)
+        kind, dt = cpu_hot_path_sample(host, ITERS)
+        cpu = {"value": PAIRS / dt, "unit": "flow frames/s", "cores": cores, "kind": kind,
+               "sample": "1 full step (1 clip: 3 builds + attention + 12 x (3 lookups + aggregate)), fp32 torch CPU, "
+                         "the reference's own core/corr.py + core/gma.py" if kind == "reference" else
+                         "1 full step of the torch CPU port (oracle/_ref absent)"}
 
     if rank == 0:
         dom = kernels["gma_aggregate"]
@@ -473,15 +802,22 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clips_per_gpu": 1, "pairs": PAIRS, "grid_1_8": [H8, W8], "D": D,
-                       "iters": ITERS, "l2": "inputs larger than L2: the step streams a 783 MB pyramid and "
+                       "iters": ITERS, "l2": "inputs larger than L2: the step streams a 805 MB pyramid and "
                        "297 MB of softmax numerators per rank, no explicit flush", "parallelism": f"clips x{world}",
-                       "launch": "cuda_graph replay of the public-API calls of one clip" if use_graph else "eager"},
-            "e2e": {"value": world * PAIRS / (ms_e2e / 1e3), "unit": "flow frames/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                       "launch": "eager public-API calls" if args.eager else
+                       "cuda_graph replay of the public-API calls of one clip (streamflow_b200.GraphedCall)"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "eager_ms_per_step": ms_eager,
+            "parity": parity,
             "roofline": {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
             "kernels": kernels,
+            "ncu_traffic_source": traffic_src,
+            "torch_gpu_baseline": torch_gpu,
+            "full_model": full_model,
+            "configs": configs,
+            "streaming": streaming,
+            "kitti_x8": kitti_x8,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "peaks": peaks["source"],
@@ -500,8 +836,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the step from a CUDA graph (streamflow_b200.GraphedCall) instead of eager calls")
+    ap.add_argument("--eager", action="store_true",
+                    help="time eager public-API calls as the headline instead of the CUDA-graph replay")
+    ap.add_argument("--graph", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--quick", action="store_true",
+                    help="hot path, parity and kernels only: skip the full-model, baseline, config and multi-GPU legs")
+    ap.add_argument("--stream-frames", type=int, default=64, help="frames of the streaming configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

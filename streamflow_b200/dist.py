@@ -57,10 +57,12 @@ def partition(n_items: int, world: int) -> List[range]:
     return out
 
 
-def gather_flows(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+def gather_flows(local: torch.Tensor, counts: Sequence[int], group=None, timings: dict | None = None) -> torch.Tensor:
     """All-gather per-rank flow stacks ``[n_r, 2, H, W]`` (n_r = counts[rank]) into ``[sum(counts), 2, H, W]``.
 
-    One ``all_gather`` of equally sized (padded) buffers -- the only collective on the path."""
+    One ``all_gather`` of equally sized (padded) buffers -- the only collective on the path.  ``timings`` (optional
+    dict) receives ``gather_events`` = a (start, stop) pair of CUDA events bracketing the collective on the current
+    stream and ``gather_bytes`` = the bytes every rank receives."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -71,13 +73,24 @@ def gather_flows(local: torch.Tensor, counts: Sequence[int], group=None) -> torc
         return local
     padded = local.new_zeros((cap,) + tuple(local.shape[1:]))
     padded[: local.shape[0]] = local
-    bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bufs, padded.contiguous(), group=group)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    # one output tensor, rank-major: all_gather_into_tensor is a single NCCL all-gather (no per-rank list copies)
+    out = padded.new_empty((world * cap,) + tuple(local.shape[1:]))
+    ev = None
+    if timings is not None and local.is_cuda:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    if ev is not None:
+        ev[1].record()
+        timings["gather_events"] = ev
+        timings["gather_bytes"] = out.numel() * out.element_size()
+    if all(c == cap for c in counts):
+        return out
+    return torch.cat([out[r * cap: r * cap + c] for r, c in enumerate(counts)], dim=0)
 
 
 def run_windows(frames: Sequence[torch.Tensor], flow_fn: Callable[[List[torch.Tensor]], List[torch.Tensor]],
-                T: int = 4, group=None) -> torch.Tensor:
+                T: int = 4, group=None, timings: dict | None = None) -> torch.Tensor:
     """Streaming inference over a frame sequence, windows sharded over the ranks of ``group``.
 
     ``flow_fn(window_frames)`` must return the T-1 flows ``[2, H, W]`` of one window (e.g. the StreamFlow model in
@@ -99,10 +112,12 @@ def run_windows(frames: Sequence[torch.Tensor], flow_fn: Callable[[List[torch.Te
     else:
         ref = frames[0]
         local = ref.new_zeros((0, 2) + tuple(ref.shape[-2:]))
-    return gather_flows(local, counts, group)
+    if timings is not None:
+        timings["windows_per_rank"] = [len(p) for p in parts]
+    return gather_flows(local, counts, group, timings)
 
 
-def run_clips(clips: Sequence, flow_fn: Callable, group=None) -> torch.Tensor:
+def run_clips(clips: Sequence, flow_fn: Callable, group=None, timings: dict | None = None) -> torch.Tensor:
     """Independent clips sharded over ranks; ``flow_fn(clip) -> Tensor[T-1, 2, H, W]``; gathered in clip order."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
@@ -117,4 +132,6 @@ def run_clips(clips: Sequence, flow_fn: Callable, group=None) -> torch.Tensor:
         raise ValueError("run_clips: flow_fn must return the same number of flows for every clip")
     local = torch.cat(outs, 0)
     counts = [len(parts[r]) * per for r in range(world)]
-    return gather_flows(local, counts, group)
+    if timings is not None:
+        timings["clips_per_rank"] = [len(p) for p in parts]
+    return gather_flows(local, counts, group, timings)

@@ -17,24 +17,30 @@ FLO_MAGIC = np.float32(202021.25)
 
 
 class InputPadder:
+    """Replicate-padding to a multiple of ``factor`` with the reference's API (``pad``, ``pad_list``, ``unpad``) and
+    its split of the padding: ``mode="sintel"`` centres it (436 rows -> 2 above, 2 below), any other mode keeps the
+    top edge and pads the bottom only (KITTI), columns are always centred.  ``_pad`` = [left, right, top, bottom]."""
+
     def __init__(self, dims, mode="sintel", factor=8):
-        self.ht, self.wd = dims[-2:]
-        pad_ht = (((self.ht // factor) + 1) * factor - self.ht) % factor
-        pad_wd = (((self.wd // factor) + 1) * factor - self.wd) % factor
-        if mode == "sintel":
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]
-        else:
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
+        height, width = int(dims[-2]), int(dims[-1])
+        self.ht, self.wd = height, width
+        extra_h, extra_w = -height % factor, -width % factor
+        left = extra_w // 2
+        top = extra_h // 2 if mode == "sintel" else 0
+        self._pad = [left, extra_w - left, top, extra_h - top]
+
+    def _apply(self, x):
+        return F.pad(x, self._pad, mode="replicate") if any(self._pad) else x
 
     def pad(self, *inputs):
-        return [F.pad(x, self._pad, mode="replicate") for x in inputs]
+        return [self._apply(x) for x in inputs]
 
     def pad_list(self, inputs):
-        return [F.pad(x, self._pad, mode="replicate") for x in inputs]
+        return [self._apply(x) for x in inputs]
 
     def unpad(self, x):
-        ht, wd = x.shape[-2:]
-        return x[..., self._pad[2]:ht - self._pad[3], self._pad[0]:wd - self._pad[1]]
+        left, right, top, bottom = self._pad
+        return x[..., top:x.shape[-2] - bottom, left:x.shape[-1] - right]
 
 
 def write_flo(path, flow) -> None:
