@@ -738,6 +738,8 @@ def run_ours(args):
 
         frames_list = list(video)
         runner.flows_on_device(video[:T])                                  # warm-up
+        if world > 1:      # the communicator's first all-gather sets up its channels (~100 ms): not part of the path
+            sfd.gather_flows(torch.zeros(1, 2, 8, 8, device=dev), [1] * world)
         tm = {}
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
