@@ -52,6 +52,14 @@ extern "C" {
                                    rounding otherwise (same mantissa as TF32)                                */
 #define SF_PREC_F16X2 1         /* hi/lo split fp16 operands, 3 tensor-core products: ~2^-21, fp32-faithful  */
 #define SF_PREC_FP32_SIMT 2     /* plain fp32 FFMA tiles + hierarchical pooling: the reference's arithmetic  */
+#define SF_PREC_AUTO 3          /* decided ON THE DEVICE by the pass that already reads every element for the
+                                   operand scale (no host sync): if every value of both feature maps is
+                                   fp16-representable (11 significant bits -- the model's mixed-precision path)
+                                   level 0 runs single-product (exact products) and the pooled levels, whose
+                                   averaged operands are not fp16-exact, run hi*hi + hi*lo; otherwise the whole
+                                   build runs as SF_PREC_F16X2.  Either way the result is fp32-faithful
+                                   (~1e-6 norm-wise vs the reference's SGEMM).  Needs D % 64 == 0 for the fast
+                                   path (else it behaves as SF_PREC_F16X2).                                   */
 
 /* dtype codes for tensors whose element type may vary */
 #define SF_DT_F32 0

@@ -16,9 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libstreamcorr.so")
 NUM_LEVELS = 4
 RADIUS = 4
 MAX_GROUPS = 8
-PREC_F16, PREC_F16X2, PREC_FP32_SIMT = 0, 1, 2
+PREC_F16, PREC_F16X2, PREC_FP32_SIMT, PREC_AUTO = 0, 1, 2, 3
 DT_F32, DT_F16, DT_BF16 = 0, 1, 2
-PRECISIONS = {"f16": PREC_F16, "f16x2": PREC_F16X2, "fp32": PREC_FP32_SIMT}
+PRECISIONS = {"f16": PREC_F16, "f16x2": PREC_F16X2, "fp32": PREC_FP32_SIMT, "auto": PREC_AUTO}
 
 KERNEL_LOOKUP, KERNEL_CORR_GEMM, KERNEL_GMA_AGGREGATE, KERNEL_GMA_STATS = 1, 2, 3, 4
 KERNEL_CORR_PACK, KERNEL_GMA_PROJ, KERNEL_GMA_FINALIZE, KERNEL_CORR_SIMT = 5, 6, 7, 8

@@ -3,6 +3,7 @@
 Same public surface as the reference (``core/corr.py:6-54``):
 
     CorrBlock(fmap1, fmap2, num_levels=4, radius=4)     # builds the 4-level correlation pyramid
+                                                        # (+ precision="auto" | "f16" | "f16x2" | "fp32")
     corr_fn(coords) -> Tensor[B, num_levels*(2r+1)**2, h, w]   fp32 contiguous
     CorrBlock.corr(fmap1, fmap2) -> Tensor[B, h, w, 1, h, w]
     attributes: num_levels, radius, corr_pyramid (list of [B*N, 1, h_l, w_l] tensors)
@@ -21,7 +22,9 @@ import torch
 from . import _lib
 from ._lib import StreamCorrError
 
-_DEFAULT_PRECISION = os.environ.get("STREAMCORR_PRECISION", "f16")
+# "auto" (include/streamcorr.h SF_PREC_AUTO): the device-side absmax pass decides -- fp16-representable feature maps (the
+# model's mixed-precision path) take the single-product fast path, anything else the fp32-faithful three-product path
+_DEFAULT_PRECISION = os.environ.get("STREAMCORR_PRECISION", "auto")
 
 
 def _aligned_workspace(nbytes: int, device) -> tuple[torch.Tensor, int]:

@@ -210,7 +210,7 @@ CorrWs corr_ws_layout(int64_t B, int64_t D, int64_t h, int64_t w, int precision)
         ws.Kp = static_cast<int>(D);
         return ws;
     }
-    ws.Kp = static_cast<int>(precision == SF_PREC_F16X2 ? 3 * D : D);
+    ws.Kp = static_cast<int>((precision == SF_PREC_F16X2 || precision == SF_PREC_AUTO) ? 3 * D : D);
     int64_t off = 0;
     ws.amax_off = off;
     off += 256;
@@ -274,8 +274,11 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     if (int rc = query_device(&di)) return rc;
     if (int rc = check_corr_shape(B, D, h, w)) return rc;
     SF_REQUIRE(fmap1 && fmap2 && levels && f1_strides && f2_strides, "corr_build: null pointer argument");
-    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2 || precision == SF_PREC_FP32_SIMT,
+    SF_REQUIRE(precision == SF_PREC_F16 || precision == SF_PREC_F16X2 || precision == SF_PREC_FP32_SIMT ||
+                   precision == SF_PREC_AUTO,
                "corr_build: unknown precision mode %d", precision);
+    // the exact-input fast path of SF_PREC_AUTO addresses k-blocks of 64: other D run the three-product mode
+    if (precision == SF_PREC_AUTO && D % 64 != 0) precision = SF_PREC_F16X2;
     for (int l = 0; l < SF_NUM_LEVELS; ++l)
         SF_REQUIRE(levels[l] && (reinterpret_cast<uintptr_t>(levels[l]) & 15) == 0,
                    "corr_build: level %d buffer is null or not 16-byte aligned", l);
@@ -310,7 +313,8 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     pp.sb[1] = f2_strides[0]; pp.sk[1] = f2_strides[1]; pp.sy[1] = f2_strides[2]; pp.sx[1] = f2_strides[3];
     pp.dst_a = reinterpret_cast<__half*>(wsb + ws.a_off);
     pp.h = (int)h; pp.w = (int)w; pp.D = (int)D;
-    pp.split = (precision == SF_PREC_F16X2);
+    pp.split = (precision == SF_PREC_F16X2) ? 1 : (precision == SF_PREC_AUTO ? 2 : 0);
+    pp.kp = ws.Kp;
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         pp.dst_b[l] = reinterpret_cast<__half*>(wsb + ws.b_off[l]);
         pp.hl[l] = g.h[l]; pp.wl[l] = g.w[l]; pp.th[l] = g.th[l]; pp.tw[l] = g.tw[l]; pp.rows[l] = (int)g.img[l];
@@ -326,6 +330,10 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
 
     CorrGemmParams gp{};
     gp.B = (int)B; gp.N = (int)N; gp.Kp = ws.Kp;
+    gp.mode = pp.split;
+    gp.kb_single = (int)((D + 63) / 64);
+    gp.kb_split = (int)((3 * D + 63) / 64);
+    gp.kb_pool = (int)((2 * D + 63) / 64);
     gp.m_tiles = (int)((N + 127) / 128);
     gp.n_tiles_total = 0;
     int n_cols[SF_NUM_LEVELS];
@@ -337,6 +345,11 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     gp.amax_bits = amax;
     gp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
 
+    // CTA pairs (cta_group::2) by default; STREAMCORR_GEMM=1cta selects the single-CTA kernel (A/B measurements)
+    static const bool pair_mode = [] {
+        const char* e = getenv("STREAMCORR_GEMM");
+        return !(e && strcmp(e, "1cta") == 0);
+    }();
     CUtensorMap tm_a, tm_b[SF_NUM_LEVELS];
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
     if (int rc = make_tmap3(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.a_off, kp, N, B, kp * 2, N * kp * 2, 64,
@@ -345,10 +358,10 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         const uint64_t rows = static_cast<uint64_t>(g.img[l]);
         if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
-                                rows * kp * 2, 64, 256, "B"))
+                                rows * kp * 2, 64, pair_mode ? 128 : 256, "B"))
             return rc;
     }
-    return launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, s);
+    return launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, pair_mode, s);
 }
 
 static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,

@@ -80,7 +80,13 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
     const CorrGemmParams& p = args.p;
     // warp index through a shuffle so the compiler knows the role dispatch is warp-uniform (see gma_sm100.cu)
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int kblocks = (p.Kp + BK - 1) / BK;
+    // k-blocks per tile: fixed by the mode, or (auto) by the exactness flag the absmax pass left on the device
+    int kb_l0 = p.kb_single, kb_lx = p.kb_single;
+    if (p.mode == 1 || (p.mode == 2 && p.amax_bits[2] != 0u)) {
+        kb_l0 = kb_lx = p.kb_split;
+    } else if (p.mode == 2) {
+        kb_lx = p.kb_pool;
+    }
 
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
     const long long t_begin = total * blockIdx.x / gridDim.x;
@@ -115,6 +121,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
             uint32_t phase = 0;
             for (long long t = t_begin; t < t_end; ++t) {
                 const TileCoord c = decode_tile(p, t);
+                const int kblocks = c.level == 0 ? kb_l0 : kb_lx;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = stage_base + stage * kStageBytes;
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
+                const int kblocks = decode_tile(p, t).level == 0 ? kb_l0 : kb_lx;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -245,10 +253,236 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_kernel(const __grid_constant
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (default): the kernel above is bound by L2 bandwidth, not by the tensor pipe or by DRAM -- per
+// 128 x 256 tile a CTA pulls 192 KB of operands through L2 (K = 256) and pushes 128 KB of results, and the measured
+// cost per streamed k-block is the same in all precision modes (~0.59 us, i.e. ~12 TB/s of aggregate L2 traffic).
+// Two CTAs of a cluster therefore share every B tile: cta_group::2 MMAs of M = 256 (each CTA owns 128 query rows and
+// its own 128 x 256 accumulator in its own TMEM) read the 256 B rows half from each CTA's shared memory, so a CTA
+// loads A (16 KB) + half of B (16 KB) per k-block instead of A + all of B (48 KB): a third less L2 operand traffic,
+// and stages of 32 KB let the ring hold 5 k-blocks.  Barrier protocol as in gma_stats_kernel: `full` lives in the
+// leader (its expect_tx arrival + the peer's remote arrival, bytes of both CTAs' TMA loads), `empty` / `tfull` are
+// signalled in both CTAs by multicast tcgen05.commit, `tempty` lives in the leader and collects the epilogue warps of
+// both CTAs.  The epilogue is the single-CTA one (each CTA stores its own 128 rows).
+namespace pair {
+constexpr int kPStages = 5;
+constexpr int kBHalfBytes = (BN / 2) * BK * 2;        // this CTA's 128 rows of the 256-row B tile
+constexpr int kPStageBytes = kABytes + kBHalfBytes;    // 32 KB
+constexpr int kPSmemBytes = kPStages * kPStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+}  // namespace pair
+
+__device__ __forceinline__ TileCoord decode_pair_tile(const CorrGemmParams& p, int pair_tiles, long long t) {
+    TileCoord c;
+    const int per_b = pair_tiles * p.n_tiles_total;
+    c.b = static_cast<int>(t / per_b);
+    const int r = static_cast<int>(t - static_cast<long long>(c.b) * per_b);
+    c.mt = r / p.n_tiles_total;                        // index of the m-tile PAIR
+    int nt = r - c.mt * p.n_tiles_total;
+    c.level = 0;
+#pragma unroll
+    for (int l = 0; l < SF_NUM_LEVELS - 1; ++l) {
+        if (c.level == l && nt >= p.n_tiles[l]) {
+            nt -= p.n_tiles[l];
+            c.level = l + 1;
+        }
+    }
+    c.ntl = nt;
+    return c;
+}
+
+__global__ void __launch_bounds__(192, 1) corr_gemm_pair_kernel(const __grid_constant__ CorrGemmArgs args) {
+    using namespace pair;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + kPStages * kPStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + kEpiBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kPStages;
+    uint64_t* tfull = bars + 2 * kPStages;
+    uint64_t* tempty = bars + 2 * kPStages + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPStages + 4);
+
+    const CorrGemmParams& p = args.p;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                  // 0 = leader of the pair
+    int kb_l0 = p.kb_single, kb_lx = p.kb_single;
+    if (p.mode == 1 || (p.mode == 2 && p.amax_bits[2] != 0u)) {
+        kb_l0 = kb_lx = p.kb_split;
+    } else if (p.mode == 2) {
+        kb_lx = p.kb_pool;
+    }
+    const int pair_tiles = (p.m_tiles + 1) / 2;
+    const long long total = static_cast<long long>(p.B) * pair_tiles * p.n_tiles_total;
+    const long long n_pairs = gridDim.x / 2, pair_id = blockIdx.x / 2;
+    const long long t_begin = total * pair_id / n_pairs;
+    const long long t_end = total * (pair_id + 1) / n_pairs;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&args.tm_a);
+        for (int l = 0; l < SF_NUM_LEVELS; ++l) tma_prefetch_desc(&args.tm_b[l]);
+        for (int i = 0; i < kPStages; ++i) {
+            mbar_init(&full[i], 2);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 2 * 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+    pdl_launch();
+    tc_fence_before();
+    cluster_sync_all();                    // both CTAs' barriers are initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = t_begin; t < t_end; ++t) {
+            const TileCoord c = decode_pair_tile(p, pair_tiles, t);
+            const int mt = 2 * c.mt + static_cast<int>(rank);   // may lie past the last m-tile: TMA zero-fills, nothing stored
+            const int kblocks = c.level == 0 ? kb_l0 : kb_lx;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = stage_base + stage * kPStageBytes;
+                if (elect_one()) {
+                    const uint32_t lead = map_shared_rank(&full[stage], 0);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * kPStageBytes);
+                    else mbar_arrive_cluster(lead);
+                    tma_load_3d_2sm(&args.tm_a, lead, sa, kb * BK, mt * BM, c.b);
+                    tma_load_3d_2sm(&args.tm_b[c.level], lead, sa + kABytes, kb * BK,
+                                    c.ntl * BN + static_cast<int>(rank) * (BN / 2), c.b);
+                }
+                __syncwarp();
+                if (++stage == kPStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {                   // the leader's elected thread issues the M = 256 MMAs for both CTAs
+            constexpr uint32_t idesc = make_idesc_f16_f32(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++local) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                const int kblocks = decode_pair_tile(p, pair_tiles, t).level == 0 ? kb_l0 : kb_lx;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + stage * kPStageBytes);
+                    const uint64_t da = make_kmajor_sw128_desc(sa);
+                    const uint64_t db = make_kmajor_sw128_desc(sa + kABytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_2sm(&empty[stage]);
+                        if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == kPStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        const int e = warp - 2;            // staging buffers of this warp
+        const int quad = warp & 3;         // TMEM lane quadrant this warp may read
+        uint8_t* bufs = epi_base + e * kEpiBufs * kEpiBuf;
+        const int e1 = scale_exponent_from_bits(p.amax_bits[0]);
+        const int e2 = scale_exponent_from_bits(p.amax_bits[1]);
+        const float alpha = p.inv_sqrt_d * exp2f(static_cast<float>(-(e1 + e2)));
+        int local = 0;
+        int buf_sel = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++local) {
+            const TileCoord c = decode_pair_tile(p, pair_tiles, t);
+            const int mt = 2 * c.mt + static_cast<int>(rank);
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = mt * BM + quad * 32;
+            const int ncols = args.n_cols[c.level];
+            const long long pitch = ncols;
+            float* out_base = args.out[c.level] + static_cast<long long>(c.b) * p.N * pitch;
+#pragma unroll 1
+            for (int cp = 0; cp < BN / 64; ++cp) {      // 64 columns per round trip through the staging buffers
+                uint32_t v0[32], v1[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + cp * 64;
+                tmem_ld_32x32(taddr, v0);
+                tmem_ld_32x32(taddr + 32, v1);
+                tmem_ld_wait();
+                if (cp == BN / 64 - 1) {   // accumulator fully drained into registers: hand TMEM back to the leader
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rank == 0) mbar_arrive(&tempty[acc]);
+                        else mbar_arrive_cluster(map_shared_rank(&tempty[acc], 0));
+                    }
+                }
+                const int col0 = c.ntl * BN + cp * 64;
+                if (col0 >= ncols || row0 >= p.N) continue;          // warp-uniform
+                uint8_t* buf = bufs + buf_sel * (2 * kEpiBuf);
+                __syncwarp();               // the read-back of this buffer pair two iterations ago is complete
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o;
+                    o.x = __uint_as_float(v0[4 * j + 0]) * alpha;
+                    o.y = __uint_as_float(v0[4 * j + 1]) * alpha;
+                    o.z = __uint_as_float(v0[4 * j + 2]) * alpha;
+                    o.w = __uint_as_float(v0[4 * j + 3]) * alpha;
+                    *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                    o.x = __uint_as_float(v1[4 * j + 0]) * alpha;
+                    o.y = __uint_as_float(v1[4 * j + 1]) * alpha;
+                    o.z = __uint_as_float(v1[4 * j + 2]) * alpha;
+                    o.w = __uint_as_float(v1[4 * j + 3]) * alpha;
+                    *reinterpret_cast<float4*>(buf + kEpiBuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+                }
+                __syncwarp();
+                const int sub = lane >> 3, chunk = lane & 7;
+                float* dst = out_base + static_cast<long long>(row0 + sub) * pitch + col0 + chunk * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + sub;
+                    const float4 a = *reinterpret_cast<const float4*>(buf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    const float4 bq = *reinterpret_cast<const float4*>(buf + kEpiBuf + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    if (row0 + rr < p.N) {        // level images are multiples of 16 floats wide: clip per 16-byte chunk
+                        float* d = dst + static_cast<long long>(4 * i) * pitch;
+                        if (col0 + chunk * 4 < ncols) __stcs(reinterpret_cast<float4*>(d), a);
+                        if (col0 + 32 + chunk * 4 < ncols) __stcs(reinterpret_cast<float4*>(d + 32), bq);
+                    }
+                }
+                buf_sel ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                    // the peer's shared memory and barriers stay valid until both are done
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<kTmemCols>(tmem_base);
+    }
+}
+
 }  // namespace
 
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
+                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms, bool pair_mode,
                      cudaStream_t s) {
     CorrGemmArgs args;
     args.tm_a = tm_a;
@@ -258,6 +492,16 @@ int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUt
         args.out[l] = levels[l];
     }
     args.p = p;
+    if (pair_mode) {        // B tensor maps must use a 64 x 128 box
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(corr_gemm_pair_kernel), pair::kPSmemBytes)) return rc;
+        const long long total = static_cast<long long>(p.B) * ((p.m_tiles + 1) / 2) * p.n_tiles_total;
+        const int grid = 2 * static_cast<int>(std::min<long long>(total, num_sms / 2));
+        prof_before(SF_KERNEL_CORR_GEMM, s);
+        SF_CUDA_CHECK(launch_kernel_cluster(corr_gemm_pair_kernel, dim3(grid), dim3(192), pair::kPSmemBytes, s, 2u, args));
+        prof_after(SF_KERNEL_CORR_GEMM, s);
+        SF_CUDA_CHECK(cudaGetLastError());
+        return SF_OK;
+    }
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(corr_gemm_kernel), kSmemBytes)) return rc;
     const long long total = static_cast<long long>(p.B) * p.m_tiles * p.n_tiles_total;
     const int grid = static_cast<int>(std::min<long long>(total, num_sms));

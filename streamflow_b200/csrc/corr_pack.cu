@@ -26,6 +26,7 @@ __global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, lo
                                long long total, unsigned* out_bits) {
     const Strided4 t = blockIdx.y == 0 ? t0 : t1;
     float m = 0.f;
+    unsigned low = 0u;       // OR of the 13 mantissa bits an fp16 cannot hold: 0 <=> every value is fp16-representable
     const int hw = h * w;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -44,11 +45,19 @@ __global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, lo
             y = n / w;
             x = n - y * w;
         }
-        m = fmaxf(m, fabsf(__ldg(t.p + b * t.sb + k * t.sk + y * t.sy + x * t.sx)));
+        const float v = __ldg(t.p + b * t.sb + k * t.sk + y * t.sy + x * t.sx);
+        m = fmaxf(m, fabsf(v));
+        low |= __float_as_uint(v) & 0x1FFFu;
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-    if ((threadIdx.x & 31) == 0) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+    for (int s = 16; s > 0; s >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+        low |= __shfl_xor_sync(0xffffffffu, low, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+        if (low) atomicOr(out_bits + 2, low);
+    }
 }
 
 // dense per-batch blocks (NCHW-contiguous or channels-last): plain vectorised sweep of the storage
@@ -60,6 +69,7 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
     const long long sb = blockIdx.y == 0 ? sb0 : sb1;
     const long long n4 = per_batch >> 2;
     float m = 0.f;
+    unsigned low = 0u;
     for (int b = 0; b < B; ++b) {
         const float4* v = reinterpret_cast<const float4*>(f + b * sb);
         const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -69,13 +79,22 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
             for (int u = 0; u < 4; ++u)     // four independent 16-byte loads in flight per thread
                 q[u] = (i + u * stride < n4) ? __ldg(v + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) {
                 m = fmaxf(fmaxf(m, fmaxf(fabsf(q[u].x), fabsf(q[u].y))), fmaxf(fabsf(q[u].z), fabsf(q[u].w)));
+                low |= (__float_as_uint(q[u].x) | __float_as_uint(q[u].y) | __float_as_uint(q[u].z) |
+                        __float_as_uint(q[u].w)) & 0x1FFFu;
+            }
         }
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+    for (int s = 16; s > 0; s >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+        low |= __shfl_xor_sync(0xffffffffu, low, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
+        if (low) atomicOr(out_bits + 2, low);
+    }
 }
 
 // CTA = one 8x8 source-pixel block x 64 channels of fmap1 (operand A) or fmap2 (operands B_0..B_3).
@@ -89,6 +108,7 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     __shared__ float t2[4][65];
     __shared__ float t3[1][65];
     __shared__ float s_scale;
+    __shared__ int s_inexact;
 
     const int tid = threadIdx.x;
     const int which = blockIdx.z & 1;              // 0: A from fmap1, 1: B levels from fmap2
@@ -99,9 +119,13 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
     const float* src = p.src[which] + b * p.sb[which];
     pdl_launch();
     pdl_wait();
-    if (tid == 0) s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[which])));
+    if (tid == 0) {
+        s_scale = exp2f(static_cast<float>(scale_exponent_from_bits(p.amax_bits[which])));
+        s_inexact = (p.split == 2) ? (p.amax_bits[2] != 0u) : (p.split == 1);
+    }
     __syncthreads();
     const float scale = s_scale;
+    const bool inexact = s_inexact != 0;
 
     const bool vec = (sk == 1) && ((sx & 3) == 0) && ((sy & 3) == 0) && ((p.sb[which] & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.src[which]) & 15) == 0) && (k0 + 64 <= p.D);
@@ -153,9 +177,13 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
         __syncthreads();
     }
 
-    const int Kp = p.split ? 3 * p.D : p.D;
+    const int Kp = p.kp;
     const int nlev = which ? SF_NUM_LEVELS : 1;
     for (int l = 0; l < nlev; ++l) {
+        // k-blocks to write behind [hi]: all three (three-product mode), or for fp16-exact inputs in auto mode only
+        // what hi*hi + hi*lo of the pooled levels needs: A's hi*2^-11 block and the lo*2^11 block of B_1..B_3
+        const bool second = inexact || (p.split == 2 && (which == 0 || l > 0));
+        const bool third = inexact;
         const int side = 8 >> l;                                   // cells per block edge at this level
         const int hl = which ? p.hl[l] : p.h, wl = which ? p.wl[l] : p.w;
         // A rows are the dense query index y*w + x; B rows follow the 4x4-tiled image layout of the pyramid
@@ -175,13 +203,13 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
             const long long m = which ? tiled_offset(v, u, p.tw[l]) : static_cast<long long>(v) * p.w + u;
             __half* drow = dst + m * Kp + k0 + kk;
             *reinterpret_cast<__half2*>(drow) = __halves2half2(h0, h1);
-            if (p.split) {
+            if (second) {
                 const float l0 = (f0 - __half2float(h0)) * 2048.f, l1 = (f1 - __half2float(h1)) * 2048.f;
                 const __half2 lo = __halves2half2(__float2half_rn(l0), __float2half_rn(l1));
                 const __half2 hs = __halves2half2(__float2half_rn(__half2float(h0) * (1.f / 2048.f)),
                                                   __float2half_rn(__half2float(h1) * (1.f / 2048.f)));
                 *reinterpret_cast<__half2*>(drow + p.D) = which ? lo : hs;
-                *reinterpret_cast<__half2*>(drow + 2 * p.D) = which ? hs : lo;
+                if (third) *reinterpret_cast<__half2*>(drow + 2 * p.D) = which ? hs : lo;
             }
         }
     }
@@ -191,7 +219,7 @@ __global__ void __launch_bounds__(256) corr_pack_kernel(const __grid_constant__ 
 
 int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
                    const int64_t s1[4], const int64_t s2[4], unsigned* amax_bits, cudaStream_t s) {
-    SF_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 2 * sizeof(unsigned), s));
+    SF_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 3 * sizeof(unsigned), s));
     Strided4 t0{f1, s1[0], s1[1], s1[2], s1[3]}, t1{f2, s2[0], s2[1], s2[2], s2[3]};
     const long long per_batch = D * h * w, total = B * per_batch;
     auto dense = [&](const int64_t st[4]) {

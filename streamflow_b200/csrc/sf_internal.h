@@ -136,11 +136,14 @@ struct PackParams {
     long long sb[2], sk[2], sy[2], sx[2];
     __half* dst_a;                       // [B, N, Kp] fp16, K contiguous
     __half* dst_b[SF_NUM_LEVELS];        // [B, th_l*tw_l*16, Kp]; row m = tiled_offset(v, u, tw_l)
-    int h, w, D, split;                  // split: Kp = 3 * D with A = [hi | hi*2^-11 | lo*2^11],
-                                         //                        B = [hi | lo*2^11 | hi*2^-11]
+    int h, w, D, split;                  // split: 0 = [hi] only; 1 = Kp = 3 * D with A = [hi | hi*2^-11 | lo*2^11],
+                                         //        B = [hi | lo*2^11 | hi*2^-11]; 2 = decided by amax_bits[2] (auto):
+                                         //        inexact inputs -> as 1, fp16-exact inputs -> A = [hi | hi*2^-11],
+                                         //        B_0 = [hi], B_l>0 = [hi | lo*2^11]
+    int kp;                              // row pitch of every packed operand in elements (D or 3 * D)
     int hl[SF_NUM_LEVELS], wl[SF_NUM_LEVELS], th[SF_NUM_LEVELS], tw[SF_NUM_LEVELS], rows[SF_NUM_LEVELS];
     int bx, by;                          // 8x8 source-pixel blocks per image
-    const unsigned* amax_bits;           // [2] absmax of fmap1, fmap2
+    const unsigned* amax_bits;           // [3] absmax bits of fmap1, fmap2; OR of the low 13 mantissa bits of all values
 };
 int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64_t h, int64_t w,
                    const int64_t s1[4], const int64_t s2[4], unsigned* amax_bits, cudaStream_t s);
@@ -153,7 +156,10 @@ int launch_corr_simt(const float* f1, const float* f2, int64_t B, int64_t D, int
 
 // ----------------------------------------------------- tcgen05 GEMM (corr_gemm_sm100.cu)
 struct CorrGemmParams {
-    int B, N, Kp;                          // batch (pairs), queries per pair, packed K (multiple of 64)
+    int B, N, Kp;                          // batch (pairs), queries per pair, packed K pitch
+    int mode;                              // 0: kb_single k-blocks everywhere; 1: kb_split; 2 (auto): amax_bits[2] != 0 ->
+                                           // kb_split, else level 0 kb_single and pooled levels kb_pool
+    int kb_single, kb_split, kb_pool;
     int m_tiles;                           // ceil(N / 128)
     int n_tiles[SF_NUM_LEVELS];            // ceil(rows_l / 256)
     int n_tiles_total;
@@ -161,7 +167,7 @@ struct CorrGemmParams {
     float inv_sqrt_d;
 };
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
+                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms, bool pair_mode,
                      cudaStream_t s);
 
 // ----------------------------------------------------------------------- GMA (gma_sm100.cu)

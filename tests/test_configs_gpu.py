@@ -243,3 +243,35 @@ def test_group_build_from_fmaps_matches_per_pair_blocks(B):
     torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
     with pytest.raises(streamflow_b200.StreamCorrError):
         CorrGroup.from_fmaps(fm[:, :1])
+
+
+def test_sintel_size_direct_parity_vs_reference_ops():
+    """BASELINE configs[1] itself -- 55x128, D=256, the 3 pairs of a T=4 clip, the bench's own inputs -- compared
+    DIRECTLY (not through properties) with the reference op sequence on the same GPU (fp32, TF32 off): full pyramids,
+    lookup features of a random-walk iteration, attention + aggregation."""
+    import bench
+    import streamflow_b200 as sfb
+    from oracle import torch_port as tp
+    torch.backends.cuda.matmul.allow_tf32 = False
+    host = bench.make_inputs(0)
+    dev = torch.device("cuda")
+    fm = host["fm_nhwc"].to(dev).permute(0, 1, 4, 2, 3)
+    coords = host["coords"].to(dev)
+    group = sfb.CorrGroup.from_fmaps(fm, radius=4)
+    feats = group([coords[5, i] for i in range(3)])
+    for i in range(3):
+        ref = tp.CpuCorrPyramid(fm[:, i], fm[:, i + 1])
+        for l in range(4):
+            got = group.blocks[i].corr_pyramid[l]
+            err = float((got - ref.levels[l]).norm() / ref.levels[l].norm())
+            assert err < 5e-6, f"pair {i} level {l}: {err:.3e}"          # fp16-exact inputs: exact products
+        want = ref(coords[5, i])
+        err = float((feats[i] - want[0]).norm() / want.norm())
+        assert err < 1e-5, f"pair {i} lookup: {err:.3e}"
+        del ref, want
+    hot = bench.HotPath(sfb, dev, host)
+    inps, mfs = host["inps"].to(dev), host["mfs"].to(dev)
+    out = hot.agg(hot.att(inps), mfs)
+    ref = tp.cpu_aggregate(tp.cpu_attention(inps, host["w_qk"].to(dev)), mfs, host["w_v"].to(dev), host["gamma"])
+    err = float(((out - mfs) - (ref - mfs)).norm() / (ref - mfs).norm())
+    assert err < 1e-3, f"gamma * attn . v at Sintel size: {err:.3e}"

@@ -15,7 +15,7 @@ from tests.helpers import coord_sets, load_golden, max_rel_err, rel_err, rs_norm
 
 pytestmark = pytest.mark.gpu
 
-TOL_BUILD = {"fp32": 1e-5, "f16x2": 2e-5, "f16": 1e-3}
+TOL_BUILD = {"fp32": 1e-5, "f16x2": 2e-5, "f16": 1e-3, "auto": 2e-5}
 SETS = ["grid", "half", "jitter", "far", "neg", "border"]
 
 
@@ -38,7 +38,7 @@ def test_lookup_on_reference_pyramid(small, name):
     assert err < 1e-5, f"lookup[{name}] rel err {err:.3e}"
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16", "auto"])
 def test_build_small_vs_reference(small, prec):
     from streamflow_b200 import CorrBlock
     blk = CorrBlock(cuda(small["f1"]), cuda(small["f2"]), precision=prec)
@@ -58,7 +58,7 @@ def test_build_small_vs_reference(small, prec):
     assert rel_err(out.cpu().numpy(), small["lookup_jitter"]) < TOL_BUILD[prec]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16", "auto"])
 def test_build_batch_strided(prec):
     """B=2, channels-last strided inputs exactly as the model passes them (streamflow.py:107,110)."""
     from streamflow_b200 import CorrBlock
@@ -74,7 +74,7 @@ def test_build_batch_strided(prec):
     assert err < TOL_BUILD[prec], f"{prec} lookup: {err:.3e}"
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x2", "f16", "auto"])
 def test_cfg1_known_answers(prec):
     """BASELINE configs[0]: D=256, 46x62 (ragged: w=62 -> pitch 64, odd pooled sizes)."""
     from streamflow_b200 import CorrBlock
@@ -108,13 +108,47 @@ def test_fp16_representable_inputs_are_exact_products():
         assert rel_err(blk.corr_pyramid[l].cpu().numpy(), pyr[l]) < 5e-4
 
 
+def test_auto_precision_picks_the_path_on_the_device():
+    """Default precision 'auto' (SF_PREC_AUTO): the absmax pass finds out on the device whether the feature maps are
+    fp16-representable.  Exact inputs -> single-product level 0 + hi*hi + hi*lo pooled levels; arbitrary fp32 inputs
+    -> the three-product path.  Both are fp32-faithful: ALL levels agree with the fp32 oracle to ~1e-6 / 2e-5."""
+    from streamflow_b200 import CorrBlock
+    f1 = rs_normal(60, (1, 128, 24, 32))
+    f2 = rs_normal(61, (1, 128, 24, 32))
+    e1, e2 = f1.astype(np.float16).astype(np.float32), f2.astype(np.float16).astype(np.float32)
+    for a, b, tol, what in ((e1, e2, 5e-6, "fp16-exact inputs"), (f1, f2, 2e-5, "arbitrary fp32 inputs"),
+                            (e1, f2, 2e-5, "one inexact operand")):
+        pyr = so.build_pyramid(a, b)
+        blk = CorrBlock(cuda(a), cuda(b))                    # default = auto
+        assert blk.precision == "auto"
+        for l in range(4):
+            err = rel_err(blk.corr_pyramid[l].cpu().numpy(), pyr[l])
+            assert err < tol, f"{what}, level {l}: {err:.3e}"
+    # D not a multiple of 64: auto falls back to the three-product mode (still fp32-faithful)
+    g1, g2 = rs_normal(62, (1, 40, 16, 20)), rs_normal(63, (1, 40, 16, 20))
+    blk = CorrBlock(cuda(g1), cuda(g2))
+    pyr = so.build_pyramid(g1, g2)
+    for l in range(4):
+        assert rel_err(blk.corr_pyramid[l].cpu().numpy(), pyr[l]) < 2e-5
+    # strided channels-last views of a clip (what the model hands over), batched group build
+    from streamflow_b200 import CorrGroup
+    fm = rs_normal(64, (1, 3, 24, 32, 64)).astype(np.float16).astype(np.float32)
+    fmaps = cuda(fm).permute(0, 1, 4, 2, 3)
+    grp = CorrGroup.from_fmaps(fmaps)
+    nchw = np.transpose(fm, (0, 1, 4, 2, 3))
+    for i in range(2):
+        pyr = so.build_pyramid(nchw[:, i], nchw[:, i + 1])
+        for l in range(4):
+            assert rel_err(grp.blocks[i].corr_pyramid[l].cpu().numpy(), pyr[l]) < 5e-6
+
+
 def test_operand_scaling_extreme_ranges():
     """Per-tensor power-of-two scaling: inputs far outside the fp16 range still give 1e-3 parity."""
     from streamflow_b200 import CorrBlock
     f1 = rs_normal(52, (1, 64, 16, 16)) * np.float32(3e4)
     f2 = rs_normal(53, (1, 64, 16, 16)) * np.float32(2e-6)
     pyr = so.build_pyramid(f1, f2)
-    for prec in ["f16", "f16x2"]:
+    for prec in ["f16", "f16x2", "auto"]:
         blk = CorrBlock(cuda(f1), cuda(f2), precision=prec)
         for l in range(4):
             err = rel_err(blk.corr_pyramid[l].cpu().numpy(), pyr[l])
