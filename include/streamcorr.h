@@ -33,7 +33,7 @@ extern "C" {
 #define SF_API
 #endif
 
-#define SF_VERSION 100          /* major*100 + minor */
+#define SF_VERSION 200          /* major*100 + minor */
 #define SF_NUM_LEVELS 4         /* corr_levels fixed by the model: core/models/streamflow.py:38 */
 #define SF_RADIUS 4             /* corr_radius fixed by the model: core/models/streamflow.py:39 */
 #define SF_MAX_GROUPS 8         /* CorrBlocks batched into one lookup launch */
@@ -80,13 +80,13 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_GMA_AGGREGATE 3
 #define SF_KERNEL_GMA_STATS 4
 #define SF_KERNEL_CORR_PACK 5
-#define SF_KERNEL_GMA_PROJ 6
+#define SF_KERNEL_GMA_PROJ 6     /* q/k projection (attention) and the per-iteration fp16 operand cast (aggregate) */
 #define SF_KERNEL_GMA_FINALIZE 7 /* retired: the aggregate kernel writes the result itself; never launched */
 #define SF_KERNEL_CORR_SIMT 8
 #define SF_KERNEL_UPSAMPLE 9
 SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
-/* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = v projection,
+/* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = fp16 operand cast,
  * bit 1 = streaming GEMM) and sf_corr_build to (bit 0 = absmax + pack, bit 1 = GEMM), so bench.py
  * can time one kernel back-to-back inside a CUDA graph.  Results are meaningless unless all bits are set (default). */
 SF_API void sf_debug_select_kernels(int gma_aggregate_mask, int corr_build_mask);
@@ -131,9 +131,12 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
  * so any run of queries is one contiguous bulk copy; pad key columns are zero; sf_gma_e_elems(P, N) is the
  * element count to allocate), and
  * sf_gma_aggregate computes every iteration
- *     out = fmap + gamma * ((E / rowsum) . (W_v . fmap)^T).
- * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) is scratch for the projections; one buffer may serve
- * the attention call and all aggregate calls on the same stream.  The aggregate is deterministic (one fp32
+ *     out = fmap + gamma * W_v . ((E / rowsum) . fmap^T)^T          (= fmap + gamma * attn . to_v(fmap), core/gma.py:94-102)
+ * i.e. the 1x1 `to_v` convolution is applied AFTER the attention-weighted sum, inside the streaming kernel: the
+ * motion features are cast to fp16 (one small launch) and streamed against E; the 128 x rows result is normalised,
+ * split into fp16 hi + lo and multiplied by W_v (fp16) with a second tensor-core GEMM in the epilogue.
+ * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) is scratch for the projections / fp16 operands; one buffer
+ * may serve the attention call and all aggregate calls on the same stream.  The aggregate is deterministic (one fp32
  * accumulator per output element, no atomics). */
 SF_API int64_t sf_gma_npad(int64_t N);
 SF_API int64_t sf_gma_e_elems(int64_t P, int64_t N);
@@ -157,8 +160,8 @@ SF_API int sf_gma_attention_qk(const void* q, const void* k, int qk_dtype, int64
                         int precision, void* E, float* rowsum, void* workspace, int64_t workspace_bytes,
                         void* stream);
 
-/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] of dtype w_dtype (SF_DT_F32, or SF_DT_F16 = weights the
- * caller converted once: the faster path, the projection rounds them to fp16 anyway); gamma: DEVICE pointer to
+/* fmap: [P, C, N] of dtype fmap_dtype; w_v: [d, C] of dtype w_dtype (SF_DT_F32 or SF_DT_F16; the tensor core
+ * consumes fp16 weights either way, as the reference's autocast does); gamma: DEVICE pointer to
  * 1 float (no host sync); out: [P, C, N] fp32 (requires C == d: the reference's `project` is None,
  * core/gma.py:86-89).                                                                                    */
 SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int fmap_dtype, const void* w_v,

@@ -68,3 +68,23 @@ def test_aggregate_streams_with_bulk_copies_and_tcgen05(sass):
 def test_lookup_is_a_cp_async_gather(sass):
     k = kernel(sass, "18corr_lookup_kernelILb0E")
     assert count(k, "LDGSTS.E.BYPASS.128") >= 16 and count(k, "UTCHMMA") == 0
+
+
+def test_correlation_gemm_default_runs_on_cta_pairs(sass):
+    """Round 2: the default correlation GEMM is the cta_group::2 kernel (M = 256, B tile shared by the pair)."""
+    k = kernel(sass, "21corr_gemm_pair_kernelE")
+    assert count(k, "UTCHMMA.2CTA") >= 4 and count(k, "UTMALDG.3D.2CTA") >= 2 and count(k, "UTCBAR.2CTA.MULTICAST") >= 2
+    assert count(k, "LDTM") >= 2 and count(k, "BRA.U.ANY") == 0
+    assert count(k, "RED.E") == 0 and count(k, "ATOMG") == 0
+
+
+def test_aggregate_applies_wv_with_a_second_tensor_core_gemm(sass):
+    """W_v is applied inside the streaming kernel: two groups of tcgen05.mma (key loop + epilogue GEMM on the staged
+    hi / lo tiles), two TMA tensor loads (X tiles, W_v), and no per-iteration mma.sync projection kernel is left."""
+    k = kernel(sass, "20gma_aggregate_kernelIfE")
+    assert count(k, "UTCHMMA") >= 4 + 16          # 4 per key block + 16 of the second GEMM
+    assert count(k, "UTMALDG") >= 3               # X ring + the two 64-column blocks of W_v
+    assert count(k, "STS.U16") >= 32              # transposed fp16 hi / lo staging of the first GEMM's result
+    assert not any("gma_proj_v_kernel" in name for name in sass)
+    cast = kernel(sass, "15gma_cast_kernelIfE")
+    assert count(cast, "HMMA") == 0 and count(cast, "F2FP") >= 4
