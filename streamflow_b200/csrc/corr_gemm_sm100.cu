@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(192, 1) corr_gemm_pair_kernel(const __grid_con
     if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_slot);
     pdl_launch();
     tc_fence_before();
+    __syncthreads();                       // CTA-local ordering of the TMEM-address write (tcgen05.alloc -> tmem_slot) that
+                                           // compute-sanitizer's racecheck can see; the cluster barrier below subsumes it
     cluster_sync_all();                    // both CTAs' barriers are initialised before any remote arrive / TMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
