@@ -60,3 +60,26 @@ def test_reference_forward_runs_on_cpu(modules):
         warnings.simplefilter("ignore")
         flows = model(frames, iters=2, test_mode=True)
     assert len(flows) == 3 and all(f.shape == (1, 2, 128, 192) and torch.isfinite(f).all() for f in flows)
+
+
+def test_input_padder_matches_the_reference_padder():
+    """streamflow_b200.flowio.InputPadder (own implementation) pads / unpads exactly like core/utils/utils.py:7-31."""
+    import importlib.util
+    import os
+    from oracle.make_ref import ref_core_dir
+    from streamflow_b200.flowio import InputPadder as Ours
+    core = ref_core_dir()
+    sys.path.insert(0, core)
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_utils", os.path.join(core, "utils", "utils.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(core)
+    for dims in [(436, 1024), (376, 1248), (1080, 1920), (37, 53), (440, 1024), (1, 3, 375, 1242)]:
+        for mode in ("sintel", "kitti"):
+            a, b = Ours(dims, mode), mod.InputPadder(dims, mode)
+            assert a._pad == b._pad, (dims, mode)
+            x = torch.arange(3 * dims[-2] * dims[-1], dtype=torch.float32).view(1, 3, dims[-2], dims[-1])
+            pa, pb = a.pad(x)[0], b.pad(x)[0]
+            assert torch.equal(pa, pb) and torch.equal(a.unpad(pa), x)
