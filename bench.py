@@ -465,6 +465,13 @@ def run_ours(args):
             return float(tt.item())
         return ms
 
+    def min_over_ranks(ms):
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            return float(tt.item())
+        return ms
+
     host = make_inputs(rank)                      # each rank owns a different clip (weak scaling)
     hot = HotPath(sfb, dev, host)
     resident = {k: host[k].to(dev) for k in ("fm_nhwc", "inps", "mfs", "coords")}
@@ -765,13 +772,17 @@ def run_ours(args):
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
         gather_ms = tm["gather_events"][0].elapsed_time(tm["gather_events"][1]) if "gather_events" in tm else 0.0
-        gather_ms = max_over_ranks(gather_ms)
+        # a rank that finishes its windows early waits inside the collective for the slowest one: the last arriver (MIN
+        # over ranks) sees the transfer itself, the MAX is transfer + load imbalance (one window = ~90 ms)
+        gather_wait_ms = max_over_ranks(gather_ms)
+        gather_ms = min_over_ranks(gather_ms)
         if tuple(flows.shape) != (n_frames - 1, 2, Hs, Ws) or not bool(torch.isfinite(flows).all()):
             raise SystemExit(f"bench.py: streaming gather returned {tuple(flows.shape)}")
         wpr = tm.get("windows_per_rank", [len(sfd.window_schedule(n_frames, T))])
         streaming = {"frames": n_frames, "windows": sum(wpr), "flows": n_frames - 1, "windows_per_rank": wpr,
                      "critical_path_windows": max(wpr), "ms_total": ms_total, "flows_per_s": (n_frames - 1) / (ms_total / 1e3),
-                     "gather_ms": gather_ms, "gather_bytes_per_rank": tm.get("gather_bytes", 0),
+                     "gather_ms": gather_ms, "gather_incl_wait_for_slowest_rank_ms": gather_wait_ms,
+                     "gather_bytes_per_rank": tm.get("gather_bytes", 0),
                      "collective": "torch.distributed all_gather_into_tensor over NCCL (inside the timed region)" if world > 1
                      else "none (1 rank)",
                      "note": "demo.py:518-532 window loop; full model per window (uint8 frames H2D, flows stay on the "
@@ -795,7 +806,8 @@ def run_ours(args):
             if tuple(kflows.shape) != (8 * PAIRS, 2, Hk, Wk):
                 raise SystemExit(f"bench.py: KITTI gather returned {tuple(kflows.shape)}")
             kitti_x8 = {"clips": 8, "clips_per_rank": tm.get("clips_per_rank", [8]), "ms_total": ms_total,
-                        "flows_per_s": 8 * PAIRS / (ms_total / 1e3), "gather_ms": max_over_ranks(gather_ms),
+                        "flows_per_s": 8 * PAIRS / (ms_total / 1e3), "gather_ms": min_over_ranks(gather_ms),
+                        "gather_incl_wait_for_slowest_rank_ms": max_over_ranks(gather_ms),
                         "gather_bytes_per_rank": tm.get("gather_bytes", 0), "scaling": "strong"}
             del kflows, clips
         torch.cuda.empty_cache()
