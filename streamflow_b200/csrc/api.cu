@@ -345,11 +345,6 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     gp.amax_bits = amax;
     gp.inv_sqrt_d = 1.0f / sqrtf(static_cast<float>(D));
 
-    // CTA pairs (cta_group::2) by default; STREAMCORR_GEMM=1cta selects the single-CTA kernel (A/B measurements)
-    static const bool pair_mode = [] {
-        const char* e = getenv("STREAMCORR_GEMM");
-        return !(e && strcmp(e, "1cta") == 0);
-    }();
     CUtensorMap tm_a, tm_b[SF_NUM_LEVELS];
     const uint64_t kp = static_cast<uint64_t>(ws.Kp);
     if (int rc = make_tmap3(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.a_off, kp, N, B, kp * 2, N * kp * 2, 64,
@@ -358,10 +353,10 @@ int sf_corr_build(const float* fmap1, const float* fmap2, int64_t B, int64_t D, 
     for (int l = 0; l < SF_NUM_LEVELS; ++l) {
         const uint64_t rows = static_cast<uint64_t>(g.img[l]);
         if (int rc = make_tmap3(&tm_b[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, wsb + ws.b_off[l], kp, rows, B, kp * 2,
-                                rows * kp * 2, 64, pair_mode ? 128 : 256, "B"))
+                                rows * kp * 2, 64, 128, "B"))
             return rc;
     }
-    return launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, pair_mode, s);
+    return launch_corr_gemm(gp, tm_a, tm_b, n_cols, levels, di.sms, s);
 }
 
 static int lookup_common(int G, const float* const* levels, const float* const* coords, void* const* out,

@@ -167,7 +167,7 @@ struct CorrGemmParams {
     float inv_sqrt_d;
 };
 int launch_corr_gemm(const CorrGemmParams& p, const CUtensorMap& tm_a, const CUtensorMap tm_b[SF_NUM_LEVELS],
-                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms, bool pair_mode,
+                     const int n_cols[SF_NUM_LEVELS], float* const levels[SF_NUM_LEVELS], int num_sms,
                      cudaStream_t s);
 
 // ----------------------------------------------------------------------- GMA (gma_sm100.cu)

@@ -41,13 +41,6 @@ def count(lines, mnemonic):
     return sum(1 for l in lines if re.search(r"\b" + re.escape(mnemonic), l))
 
 
-def test_correlation_gemm_is_a_tcgen05_tma_kernel(sass):
-    k = kernel(sass, "16corr_gemm_kernelE")
-    assert count(k, "UTCHMMA") >= 4 and count(k, "UTMALDG") >= 2 and count(k, "LDTM") >= 2 and count(k, "UTCBAR") >= 2
-    assert count(k, "BRA.U.ANY") == 0           # warp-uniform issue: no waterfall around MMA / TMA instructions
-    assert count(k, "STS") >= 8 and count(k, "ST.E.128 desc") == 0     # staging uses shared-space stores
-
-
 def test_attention_kernel_runs_on_cta_pairs(sass):
     k = kernel(sass, "16gma_stats_kernelE")
     assert count(k, "UTCHMMA.2CTA") >= 24       # cta_group::2 MMAs (the unrolled [hi | lo] schedule)
@@ -76,6 +69,8 @@ def test_correlation_gemm_default_runs_on_cta_pairs(sass):
     assert count(k, "UTCHMMA.2CTA") >= 4 and count(k, "UTMALDG.3D.2CTA") >= 2 and count(k, "UTCBAR.2CTA.MULTICAST") >= 2
     assert count(k, "LDTM") >= 2 and count(k, "BRA.U.ANY") == 0
     assert count(k, "RED.E") == 0 and count(k, "ATOMG") == 0
+    assert count(k, "STS") >= 8 and count(k, "ST.E.128 desc") == 0     # staging uses shared-space stores
+    assert not any("16corr_gemm_kernelE" in name for name in sass)     # the single-CTA kernel of round 1 is gone
 
 
 def test_aggregate_applies_wv_with_a_second_tensor_core_gemm(sass):
