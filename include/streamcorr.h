@@ -81,7 +81,6 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_GMA_STATS 4
 #define SF_KERNEL_CORR_PACK 5
 #define SF_KERNEL_GMA_PROJ 6     /* q/k projection (attention) and the per-iteration fp16 operand cast (aggregate) */
-#define SF_KERNEL_GMA_FINALIZE 7 /* retired: the aggregate kernel writes the result itself; never launched */
 #define SF_KERNEL_CORR_SIMT 8
 #define SF_KERNEL_UPSAMPLE 9
 SF_API int64_t sf_launch_count(void);

@@ -21,7 +21,7 @@ DT_F32, DT_F16, DT_BF16 = 0, 1, 2
 PRECISIONS = {"f16": PREC_F16, "f16x2": PREC_F16X2, "fp32": PREC_FP32_SIMT, "auto": PREC_AUTO}
 
 KERNEL_LOOKUP, KERNEL_CORR_GEMM, KERNEL_GMA_AGGREGATE, KERNEL_GMA_STATS = 1, 2, 3, 4
-KERNEL_CORR_PACK, KERNEL_GMA_PROJ, KERNEL_GMA_FINALIZE, KERNEL_CORR_SIMT = 5, 6, 7, 8
+KERNEL_CORR_PACK, KERNEL_GMA_PROJ, KERNEL_CORR_SIMT, KERNEL_UPSAMPLE = 5, 6, 8, 9
 
 EXPORTS = [
     "sf_version", "sf_last_error", "sf_device_ok", "sf_launch_count", "sf_profile_kernel",
