@@ -693,13 +693,18 @@ def run_ours(args):
         tf = flops / us / 1e6
         peak_tf = peaks["bf16_tflops"]
         out_bytes = PAIRS * 4 * N * sum(((H8 >> l) + 3) // 4 * (((W8 >> l) + 3) // 4) * 16 for l in range(4))
-        kernels["corr_gemm"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
-                                "frac": tf / peak_tf, "us_per_launch": us,
-                                "us_per_launch_event_pairs_in_step": us_ev, "launches_timed": n,
-                                "algorithmic_flops": flops, "store_bytes": out_bytes, "store_gbs": out_bytes / us / 1e3,
-                                "store_frac_of_hbm": out_bytes / us / 1e3 / hbm, "traffic": traffic.get("corr_gemm"),
-                                "note": "one launch = the %d pairs of the clip; fp16 operands (kind::f16), fp32 accumulate; "
-                                        "output-store bound: store_frac_of_hbm is the binding roofline" % PAIRS}
+        # Primary roofline = HBM writes (the kernel stores 805 MB per launch against 76 GFLOP: 20 us of MMA vs 42 us of
+        # stores per pair); the tensor-pipe view north_star names is reported beside it (ncu: 39 % active in this mode,
+        # 58 % in the three-product mode, profiles/r2_ncu_full_summary.md).
+        write_probe = 5880.0      # GB/s, scripts/probes/store_probe.cu on this pool (profiles/r1d_probes.txt)
+        kernels["corr_gemm"] = {"bound": "hbm", "achieved": out_bytes / us / 1e3, "peak": hbm, "unit": "GB/s",
+                                "frac": out_bytes / us / 1e3 / hbm, "frac_of_write_probe": out_bytes / us / 1e3 / write_probe,
+                                "us_per_launch": us, "us_per_launch_event_pairs_in_step": us_ev, "launches_timed": n,
+                                "algorithmic_bytes": out_bytes, "traffic": traffic.get("corr_gemm"),
+                                "algorithmic_flops": flops, "tensor_tflops": tf, "tensor_frac": tf / peak_tf,
+                                "tensor_pipe_active_pct_ncu": {"auto_exact_inputs": 39.2, "f16x2": 58.1},
+                                "note": "one launch = the %d pairs of the clip; precision auto on fp16-exact inputs (single-product "
+                                        "level 0, hi*hi + hi*lo pooled levels), CTA pairs (cta_group::2), fp32 accumulate" % PAIRS}
         kernels["gma_cast"] = {"us_per_launch": us_graph["gma_cast"]}
         for name, kind in (("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
             us, n = kernel_time(kind)
