@@ -667,6 +667,15 @@ def run_ours(args):
                 lambda i: g_group([resident["coords"][i % ITERS, j] for j in range(PAIRS)]), ITERS),
             "corr_gemm": graph_kernel_time(lambda i: sfb.CorrGroup.from_fmaps(fm_views, radius=4), 4, corr_mask=2),
         }
+        # launch-size dependence of the lookup: the same kernel over 1 and 8 pairs per launch (8 = SF_MAX_GROUPS, a T = 9
+        # clip) separates a fixed per-launch cost (launch, pipeline fill, tail) from the streaming rate
+        g1 = sfb.CorrGroup(g_group.blocks[:1])
+        us_lk1 = graph_kernel_time(lambda i: g1([resident["coords"][i % ITERS, 0]]), ITERS)
+        fm9 = torch.cat([fm_views, fm_views, fm_views[:, :1]], dim=1)                   # 9 frames -> 8 pairs
+        g8 = sfb.CorrGroup.from_fmaps(fm9, radius=4)
+        c8 = [resident["coords"][:, j % PAIRS] for j in range(8)]
+        us_lk8 = graph_kernel_time(lambda i: g8([c8[j][i % ITERS] for j in range(8)]), ITERS)
+        del g1, g8, fm9
         del g_group, g_handle
         us, n = kernel_time(_lib.KERNEL_GMA_AGGREGATE)
         npad = L.sf_gma_npad(N)
@@ -686,7 +695,14 @@ def run_ours(args):
                                   "frac": bytes_lk / ug / 1e3 / hbm, "us_per_launch": ug,
                                   "us_per_launch_event_pairs_in_step": us, "launches_timed": n,
                                   "algorithmic_bytes": bytes_lk, "traffic": traffic.get("corr_lookup"),
-                                  "note": "3 pairs per launch, coords random-walk; pyramid 805 MB >> L2"}
+                                  "note": "3 pairs per launch, coords random-walk; pyramid 805 MB >> L2",
+                                  "launch_size": {"us_1_pair": us_lk1, "us_3_pairs": ug, "us_8_pairs": us_lk8,
+                                                  "us_per_extra_pair": (us_lk8 - us_lk1) / 7.0,
+                                                  "frac_8_pairs": 2904 * 8 * N / us_lk8 / 1e3 / hbm,
+                                                  "frac_marginal": 2904 * N / ((us_lk8 - us_lk1) / 7.0) / 1e3 / hbm,
+                                                  "note": "1 / 3 / 8 pairs per launch: the rate per extra pair does not improve "
+                                                          "with launch size, i.e. the gather itself (51 G 64-byte blocks/s), not a "
+                                                          "fixed per-launch cost, sets the fraction"}}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D * PAIRS                     # one launch builds the pyramids of all pairs
         us_ev, us = us, us_graph["corr_gemm"]
