@@ -135,8 +135,10 @@ SF_API int sf_corr_lookup_group(int G, const float* const* levels, const float* 
  * motion features are cast to fp16 (one small launch) and streamed against E; the 128 x rows result is normalised,
  * split into fp16 hi + lo and multiplied by W_v (fp16) with a second tensor-core GEMM in the epilogue.
  * `workspace` (sf_gma_workspace_bytes, 1024-byte aligned) is scratch for the projections / fp16 operands; one buffer
- * may serve the attention call and all aggregate calls on the same stream.  The aggregate is deterministic (one fp32
- * accumulator per output element, no atomics). */
+ * serves the attention call and all aggregate calls that use its E on the same stream (it also carries one word of
+ * state: "E is settled", which lets the second and later aggregate launches start streaming E before the kernel
+ * launched in front of them has finished; with any other workspace the aggregate simply waits).  The aggregate is
+ * deterministic (one fp32 accumulator per output element, no atomics). */
 SF_API int64_t sf_gma_npad(int64_t N);
 SF_API int64_t sf_gma_e_elems(int64_t P, int64_t N);
 SF_API int64_t sf_gma_workspace_bytes(int64_t P, int64_t C, int64_t N, int64_t d);

@@ -70,7 +70,22 @@ struct GmaAggArgs {
     int fbuf_pitch;                 // > 0: single-segment CTAs; the fmap tile is prefetched into shared memory
     int fbuf_off;                   // byte offset of that tile inside the ring area
     int dbg;                        // STREAMCORR_AGG_DEBUG ablation bits (measurement only; results are wrong when set)
+    // Early E stream.  E is written once per clip by the attention kernels and then only read, so from the SECOND
+    // aggregate call on a handle it cannot depend on the kernel launched right before this one (the operand cast): the E
+    // producer then skips griddepcontrol.wait and fills its ring (147 KB per SM) while the predecessor is still running.
+    // `settled` (a word in the GMA workspace) is cleared by sf_gma_attention* and set to kSettledMagic by the end of
+    // every aggregate launch; a launch that reads anything else -- the first after an attention call, whose stats kernels
+    // may still be running under programmatic dependent launch, or a workspace the attention call never saw -- waits
+    // like every other warp.
+    unsigned* settled;
 };
+constexpr unsigned kSettledMagic = 0x5E771ED1u;
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 struct Seg {
     int pb, row0, rows;
@@ -217,7 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
+    // every role but (possibly) the E producer depends on the preceding kernel (the fp16 cast of X, the fmap itself)
+    bool e_early = false;
+    if (warp == 0) {
+        unsigned st = 0;
+        if (lane == 0 && args.settled != nullptr) st = ld_acquire_gpu_u32(args.settled);
+        e_early = __shfl_sync(0xffffffffu, st, 0) == kSettledMagic;
+    }
+    if (!e_early) pdl_wait();
 
     if (warp == 0) {
         {                                                      // ---- E producer (warp-uniform loop, elected issue)
@@ -509,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) gma_aggregate_kernel(const __grid
         tc_fence_after();
         tmem_dealloc<kTmemCols>(tmem_base);
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && args.settled != nullptr) *args.settled = kSettledMagic;
 }
 
 template <typename T>
@@ -524,11 +547,16 @@ int launch_typed(const GmaAggArgs& args, int grid, cudaStream_t s) {
 }  // namespace
 
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_w, int num_sms,
-                         cudaStream_t s) {
+                         unsigned* settled, cudaStream_t s) {
     GmaAggArgs args;
     args.tm_v = tm_x;
     args.tm_w = tm_w;
     args.p = p;
+    static const bool want_early = [] {
+        const char* e = getenv("STREAMCORR_AGG_EARLY_E");
+        return !(e && e[0] == '0');
+    }();
+    args.settled = want_early ? settled : nullptr;
     args.units_per_map = (p.N + kUnit - 1) / kUnit;
     const long long U = static_cast<long long>(p.P) * args.units_per_map;
     const int grid = static_cast<int>(std::min<long long>(U, num_sms));

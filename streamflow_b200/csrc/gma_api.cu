@@ -5,7 +5,7 @@ namespace sf {
 namespace {
 
 struct GmaWs {
-    int64_t q_off, k_off, rowmax_off, rowsum_fx_off, x16_off, w16_off, eye_off, total;
+    int64_t q_off, k_off, rowmax_off, rowsum_fx_off, x16_off, w16_off, eye_off, flag_off, total;
     int Kp;
     int64_t Npad;
 };
@@ -22,6 +22,7 @@ GmaWs gma_ws_layout(int64_t P, int64_t N, int64_t d) {
     ws.x16_off = off;     off += align_up(P * d * ws.Npad * 2, 1024);
     ws.w16_off = off;     off += align_up(d * d * 2, 1024);
     ws.eye_off = off;     off += align_up(d * d * 4, 1024);
+    ws.flag_off = off;    off += 1024;          // "E is settled" word of the aggregate's early E stream
     ws.total = off;
     return ws;
 }
@@ -54,6 +55,8 @@ int attention_common(const void* xq, const void* xk, int x_dtype, const float* w
     const int split = (precision == SF_PREC_F16X2);
     const int Kp = split ? ws.Kp : static_cast<int>(d);
     const int64_t Npad = ws.Npad;
+    // E is about to be rewritten: the next aggregate launch on this workspace must wait for its predecessors
+    SF_CUDA_CHECK(cudaMemsetAsync(wsb + ws.flag_off, 0, 1024, s));
 
     GmaProjParams pq{};
     pq.x = xq; pq.x_dtype = x_dtype; pq.w = w_q;
@@ -182,7 +185,8 @@ int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap, int f
     ap.out = out;
     ap.e_ptr = static_cast<const __half*>(E);
     ap.e_map_stride = e_rows * 64;
-    return (parts & 2) ? launch_gma_aggregate(ap, tm_x, tm_w, di.sms, s) : SF_OK;
+    return (parts & 2) ? launch_gma_aggregate(ap, tm_x, tm_w, di.sms, reinterpret_cast<unsigned*>(wsb + ws.flag_off), s)
+                       : SF_OK;
 }
 
 }  // extern "C"

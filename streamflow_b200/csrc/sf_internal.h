@@ -225,8 +225,9 @@ struct GmaAggParams {
     const __half* e_ptr;        // tile-major E (swizzled 16 KB blocks) and its per-map stride in elements
     long long e_map_stride;
 };
+// `settled`: one word of the GMA workspace, 0 after sf_gma_attention*, set by every aggregate launch (see the kernel)
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_w, int num_sms,
-                         cudaStream_t s);
+                         unsigned* settled, cudaStream_t s);
 int launch_gma_identity(float* dst, int d, cudaStream_t s);      // dst[d, d] <- I
 
 int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
