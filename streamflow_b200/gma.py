@@ -9,7 +9,9 @@ reference checkpoints load unchanged (``to_qk.weight [2*inner, dim, 1, 1]``, ``t
 
 ``Attention.forward`` returns an opaque ``AttentionHandle`` instead of the dense ``[P, 1, N, N]`` fp32 matrix
 (the callers only pass it on to ``Aggregate``): it owns the fp16 softmax numerators E, their row sums and the
-workspace.  ``handle.dense()`` materialises the reference-shaped matrix for tests.
+workspace.  ``handle.dense()`` materialises the reference-shaped matrix for tests.  ``Aggregate.forward`` streams the
+motion features against E and applies ``to_v`` AFTER the attention-weighted sum inside the same kernel
+(``sum_j (W_v x)_j a_ij = W_v (sum_j x_j a_ij)``), so no per-iteration projection launch exists.
 
 The authors' memory-saving convention (``demo.py:235-282``, ``test_memory.py:240-282``) is accepted too:
 ``Attention(..., return_qk=True)`` returns the projected ``(q, k)`` like their ``Attention`` and
@@ -226,7 +228,7 @@ class Aggregate(nn.Module):
             x = x.contiguous()
         P, C, h, w = x.shape
         dev = x.device
-        # the projection runs on fp16 tensor-core operands: convert the weights once, not once per CTA per call
+        # W_v enters the in-kernel tensor-core GEMM as fp16 (as under the reference's autocast): convert once per weight update
         wv = _weight_2d(self, "_wv_cache", self.to_v.weight, self.dim_head, C, torch.float16)
         gamma = self.gamma
         if gamma.dtype != torch.float32:
