@@ -45,3 +45,63 @@ class GraphedCall:
     def __call__(self):
         self.graph.replay()
         return self.result
+
+
+class GraphedModel:
+    """Whole-forward CUDA-graph replay of an (unmodified) StreamFlow model running on the B200 operators.
+
+    The reference's own ``CorrBlock.__call__`` builds its sampling grid on the host and synchronises 144 times per
+    forward, so its forward cannot be captured; with ``streamflow_b200.install()`` the only host-side
+    piece left inside ``SKFlow_MF8.forward`` is ``coords_grid(...).to(device)`` (``core/models/streamflow.py:74-80``,
+    a pageable host-to-device copy).  During warm-up and capture the model module's ``coords_grid`` is bound to a
+    device-resident equivalent (same values, ``core/utils/utils.py:82-85``); nothing else of the caller is touched.
+    The ~3000 eager kernel launches of one T = 4, 12-iteration forward then replay as ONE graph launch.
+
+        gm = GraphedModel(model, (T, 3, H, W), iters=12)      # model: SKFlow_MF8 after install(), .eval(), on a GPU
+        flows = gm(frames_u8)                                  # [T, 3, H, W] uint8 (host or device) -> [T-1, 2, H, W]
+
+    ``frames`` are copied into the graph's static input; the returned tensor is the graph's static output (overwritten
+    by the next call).  Padding to a multiple of 8 follows the reference's ``InputPadder`` ('sintel' or 'kitti' mode).
+    """
+
+    def __init__(self, model, frames_shape, iters: int = 12, pad_mode: str = "sintel", warmup: int = 2):
+        import sys
+
+        from .corr import coords_grid as device_coords_grid
+        from .flowio import InputPadder
+
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise _lib.StreamCorrError("GraphedModel: the model must live on a CUDA device")
+        if model.training:
+            raise _lib.StreamCorrError("GraphedModel: inference only, call model.eval() first")
+        dev = p.device
+        T, C, H, W = (int(v) for v in frames_shape)
+        self.model, self.iters, self.device = model, int(iters), dev
+        self.frames = torch.zeros((T, C, H, W), dtype=torch.uint8, device=dev)
+        padder = InputPadder((H, W), mode=pad_mode)
+        mod = sys.modules.get(model.__class__.__module__)
+
+        def dev_grid(batch, ht, wd):
+            return device_coords_grid(batch, ht, wd, device=dev)
+
+        def fn():
+            frames = [f[None].float() for f in self.frames]
+            out = model(padder.pad_list(frames), iters=self.iters, test_mode=True)
+            return torch.cat([padder.unpad(o) for o in out], 0).contiguous()
+
+        saved = getattr(mod, "coords_grid", None) if mod is not None else None
+        if saved is not None:
+            mod.coords_grid = dev_grid
+        try:
+            with torch.cuda.device(dev), torch.no_grad():
+                inner = GraphedCall(fn, warmup=warmup, device=dev)
+        finally:
+            if saved is not None:
+                mod.coords_grid = saved
+        self._inner = inner
+        self.launches = inner.launches
+
+    def __call__(self, frames_u8):
+        self.frames.copy_(frames_u8, non_blocking=True)
+        return self._inner()
