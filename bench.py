@@ -524,13 +524,29 @@ def run_ours(args):
         frames_host = make_frames(T, Hs, Ws, 100 + rank).pin_memory()
         runner = FullModelRunner(our_model, dev, Hs, Ws)
         k_e2e = max(3, min(args.steps, 10))
-        ms_e2e = max_over_ranks(_time_events(lambda: runner(frames_host), k_e2e, 3, barrier))
+        ms_e2e_eager = max_over_ranks(_time_events(lambda: runner(frames_host), k_e2e, 3, barrier))
+        # public API for a stream of equally shaped clips: the whole forward of the unmodified model replayed as ONE CUDA
+        # graph (possible because the B200 operators never synchronise or touch the host; the reference's own CorrBlock
+        # builds its sampling grid on the host every lookup)
+        gm = sfb.GraphedModel(our_model, (T, 3, Hs, Ws), iters=ITERS)
+        e2e_host_flows = torch.empty((PAIRS, 2, Hs, Ws), dtype=torch.float32).pin_memory()
+
+        def step_e2e_graph():
+            e2e_host_flows.copy_(gm(frames_host), non_blocking=True)
+
+        ms_e2e = max_over_ranks(_time_events(step_e2e_graph, k_e2e, 3, barrier))
+        graph_diff = float((gm(frames_host) - runner.flows_on_device(frames_host)).abs().max())
+        if not graph_diff < 1e-3:
+            raise SystemExit(f"bench.py: graph replay of the full model differs from the eager forward by {graph_diff} px")
         e2e = {"value": world * PAIRS / (ms_e2e / 1e3), "unit": "flow frames/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": runner.h2d, "d2h_bytes_per_step": runner.d2h, "steps": k_e2e,
+               "eager_ms_per_step": ms_e2e_eager, "graph_vs_eager_max_abs_px": graph_diff,
                "workload": "sintel_436x1024_T4_12iters_full_model",
+               "launch": "cuda_graph replay of the whole forward (streamflow_b200.GraphedModel)",
                "note": "uint8 frames from pinned host memory -> unmodified reference model (oracle/_ref SKFlow_MF8 / "
-                       "SKUpdateBlock_TAM_v3 / Twins_CSC, eager PyTorch, fp16 autocast) on the B200 operators via "
+                       "SKUpdateBlock_TAM_v3 / Twins_CSC, fp16 autocast) on the B200 operators via "
                        "streamflow_b200.install() -> full-resolution flows to pinned host memory"}
+        ms_e2e_graph, ms_e2e = ms_e2e, ms_e2e_eager        # the same-GPU comparison below is eager against eager
         if rank == 0 and world == 1:
             ref_runner = FullModelRunner(ref_model, dev, Hs, Ws)
             ms_ref = _time_events(lambda: ref_runner(frames_host), k_e2e, 3, barrier)
@@ -540,6 +556,7 @@ def run_ours(args):
             full_model = {"b200_l1_ms": ms_e2e, "reference_l1_ms": ms_ref,
                           "b200_l1_flows_per_s": PAIRS / (ms_e2e / 1e3), "reference_l1_flows_per_s": PAIRS / (ms_ref / 1e3),
                           "speedup": ms_ref / ms_e2e, "hot_path_share_b200": ms_eager / ms_e2e,
+                          "b200_l1_graph_ms": ms_e2e_graph, "speedup_graph": ms_ref / ms_e2e_graph,
                           "mean_epe_px_per_pair": [float(x) for x in epe],
                           "flow_magnitude_px": float(torch.sqrt((fr ** 2).sum(1)).mean()),
                           "note": "whole forward incl. H2D of frames and D2H of flows, same GPU, same random-init weights "
@@ -774,13 +791,14 @@ def run_ours(args):
         Hs, Ws = SHAPES["sintel_436x1024"][:2]
         n_frames = args.stream_frames
         video = make_frames(n_frames, Hs, Ws, 0).pin_memory()            # identical on every rank
-        runner = FullModelRunner(our_model, dev, Hs, Ws)
+        if "gm" not in locals():
+            gm = sfb.GraphedModel(our_model, (T, 3, Hs, Ws), iters=ITERS)
 
-        def flow_fn(window):
-            return list(runner.flows_on_device(torch.stack(window)))
+        def flow_fn(window):          # graph replay per window; the static output is overwritten by the next replay
+            return list(gm(torch.stack(window)).clone())
 
         frames_list = list(video)
-        runner.flows_on_device(video[:T])                                  # warm-up
+        gm(video[:T])                                                      # warm-up
         if world > 1:      # the communicator's first all-gather sets up its channels (~100 ms): not part of the path
             sfd.gather_flows(torch.zeros(1, 2, 8, 8, device=dev), [1] * world)
         tm = {}
@@ -806,6 +824,7 @@ def run_ours(args):
                      "gather_bytes_per_rank": tm.get("gather_bytes", 0),
                      "collective": "torch.distributed all_gather_into_tensor over NCCL (inside the timed region)" if world > 1
                      else "none (1 rank)",
+                     "launch": "one CUDA-graph replay of the whole forward per window (streamflow_b200.GraphedModel)",
                      "note": "demo.py:518-532 window loop; full model per window (uint8 frames H2D, flows stay on the "
                              "device until the gather; rank 0 copies the 63 flows to the host inside the timed region)"}
         del flows, host_flows, video, frames_list
@@ -813,13 +832,13 @@ def run_ours(args):
         if world <= 8:
             Hk, Wk = SHAPES["kitti_376x1248"][:2]
             clips = [make_frames(T, Hk, Wk, s).pin_memory() for s in range(8)]
-            krunner = FullModelRunner(our_model, dev, Hk, Wk)
-            krunner.flows_on_device(clips[0])
+            kgm = sfb.GraphedModel(our_model, (T, 3, Hk, Wk), iters=ITERS, pad_mode="kitti")
+            kgm(clips[0])
             tm = {}
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            kflows = sfd.run_clips(clips, krunner.flows_on_device, timings=tm)
+            kflows = sfd.run_clips(clips, lambda clip: kgm(clip).clone(), timings=tm)
             e1.record()
             barrier()
             ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -829,8 +848,9 @@ def run_ours(args):
             kitti_x8 = {"clips": 8, "clips_per_rank": tm.get("clips_per_rank", [8]), "ms_total": ms_total,
                         "flows_per_s": 8 * PAIRS / (ms_total / 1e3), "gather_ms": min_over_ranks(gather_ms),
                         "gather_incl_wait_for_slowest_rank_ms": max_over_ranks(gather_ms),
-                        "gather_bytes_per_rank": tm.get("gather_bytes", 0), "scaling": "strong"}
-            del kflows, clips
+                        "gather_bytes_per_rank": tm.get("gather_bytes", 0), "scaling": "strong",
+                        "launch": "one CUDA-graph replay of the whole forward per clip (streamflow_b200.GraphedModel)"}
+            del kflows, clips, kgm
         torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's own operators on this host's cores

@@ -8,9 +8,9 @@ resolve to these classes so the unchanged StreamFlow model code runs on them).
 from ._lib import StreamCorrError, lib  # noqa: F401
 from .corr import CorrBlock, CorrGroup, coords_grid  # noqa: F401
 from .gma import Aggregate, Attention, AttentionHandle  # noqa: F401
-from .graph import GraphedCall  # noqa: F401
+from .graph import GraphedCall, GraphedModel  # noqa: F401
 from .install import install, uninstall  # noqa: F401
 from .upsample import patch_upsample, upsample_flow  # noqa: F401
 
 __all__ = ["CorrBlock", "CorrGroup", "coords_grid", "Attention", "Aggregate", "AttentionHandle", "install",
-           "uninstall", "upsample_flow", "patch_upsample", "StreamCorrError", "lib", "GraphedCall"]
+           "uninstall", "upsample_flow", "patch_upsample", "StreamCorrError", "lib", "GraphedCall", "GraphedModel"]

@@ -29,202 +29,369 @@ namespace sf {
 
 namespace {
 
-constexpr int kQ = 32;              // queries per CTA
-constexpr int kRowFloats = 16;      // 4 tile columns of 4 floats per staged row
+constexpr int kQ = 32;              // queries per work item
 constexpr int kRows = 2 * SF_RADIUS + 2;                 // 10 window rows / columns
-constexpr int kWinStride = kRows * kRowFloats + 4;       // 164 floats: 8 consecutive queries -> distinct bank quads
 constexpr int kSide = 2 * SF_RADIUS + 1;                 // 9
-
-// 16-byte async copy, zero-filled when !pred.  The L2 evict_last policy keeps the window tiles resident for the
-// next refinement iteration (flow moves by ~1 px; a warm-cache ncu capture shows 27 % fewer DRAM bytes than cold)
-// while the 300 MB softmax stream of the aggregation passes through L2 as evict_first.
-template <bool kViaL1>
-__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool pred, unsigned long long policy) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst));
-    const int bytes = pred ? 16 : 0;
-    if constexpr (kViaL1)       // through L1: the four 16-byte requests of a lane quad merge into one 64-byte L2 request
-        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(d), "l"(src), "r"(bytes),
-                     "l"(policy)
-                     : "memory");
-    else
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(d), "l"(src), "r"(bytes),
-                     "l"(policy)
-                     : "memory");
-}
+constexpr int kThreads = 128;       // 4 warps: a loader quad per query, 4 row groups in stage C (256 threads = loader octets and
+                                    // 8 row groups were measured: 18.7 us against 16.8 us, the extra row loads of stage C cost more)
 
 // Per-item metadata for stage C, written by one lane of each loader quad.
 struct Meta {
     float ax[kQ], ay[kQ];
     int o[kQ];                   // x0 & 3: window origin inside its first tile column; -1: query out of range
     unsigned out_off[kQ];        // element offset of out[b, lvl*81, n] inside the group's output tensor
-    int grp, lvl;
+    int grp;
 };
 
+// What every CTA knows about its share of the work.  The grid is a multiple of 4 CTAs: CTA c owns ONE pyramid level
+// (c & 3) and the (group, 32-query tile) pairs t = c / 4 + k * gridDim / 4, so every level-dependent quantity is
+// loop-invariant and the item -> (group, tile) mapping advances incrementally (no division).
+struct Cta {
+    int lvl, tstep, t_total, tiles, BN, th, tw, img, row_step;
+    float inv, xmax, ymax;
+    int t, grp, tile;            // the item whose coordinates are loaded next
+    __device__ __forceinline__ void init(const LookupParams& p) {
+        lvl = blockIdx.x & 3;
+        tstep = gridDim.x >> 2;
+        t_total = static_cast<int>(p.items >> 2);           // groups * tiles
+        tiles = static_cast<int>(p.tiles);
+        BN = static_cast<int>(p.BN);
+        th = p.th[lvl];
+        tw = p.tw[lvl];
+        img = static_cast<int>(p.img[lvl]);
+        row_step = tw * 16;                                  // floats between vertically adjacent tiles
+        inv = 1.0f / static_cast<float>(1 << lvl);
+        xmax = static_cast<float>(p.wl[lvl] + 8);
+        ymax = static_cast<float>(p.hl[lvl] + 8);
+        t = tile = blockIdx.x >> 2;
+        grp = 0;
+        normalise();
+    }
+    __device__ __forceinline__ void normalise() {
+        while (tile >= tiles && grp < SF_MAX_GROUPS - 1) {
+            tile -= tiles;
+            ++grp;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+        t += tstep;
+        tile += tstep;
+        normalise();
+    }
+};
+
+// stage A: coordinates of one query of item (c.t, c.grp, c.tile) into registers
+struct Pending {
+    float cx, cy;
+    int grp, qid, b, n;
+};
+__device__ __forceinline__ void load_coords(const LookupParams& p, const Cta& c, int lq, Pending& pd) {
+    pd.cx = pd.cy = -1e30f;
+    pd.qid = -1;
+    pd.grp = c.grp;
+    pd.b = pd.n = 0;
+    const int qid = c.tile * kQ + lq;
+    if (c.t < c.t_total && qid < c.BN) {
+        pd.qid = qid;
+        pd.b = (p.N >= c.BN) ? 0 : static_cast<int>(static_cast<unsigned>(qid) / static_cast<unsigned>(p.N));
+        pd.n = qid - pd.b * p.N;
+        const float* g = p.coords[c.grp] + static_cast<long long>(pd.b) * 2 * p.N + pd.n;
+        pd.cx = __ldg(g);
+        pd.cy = __ldg(g + p.N);
+    }
+}
+
+// Integer window origin (x0, y0) and the single fractional pair shared by all 81 taps of the level (window offsets are
+// integers).  Far outside the image every tap is zero; clamping keeps the int conversion defined (NaN / missing
+// coordinates clamp to the lower bound and yield zeros).
+struct Origin {
+    int x0, y0;
+    float ax, ay;
+};
+__device__ __forceinline__ Origin window_origin(const Cta& c, const Pending& pd) {
+    const float X0 = fminf(fmaxf(fmaf(pd.cx, c.inv, -static_cast<float>(SF_RADIUS)), -16.f), c.xmax);
+    const float Y0 = fminf(fmaxf(fmaf(pd.cy, c.inv, -static_cast<float>(SF_RADIUS)), -16.f), c.ymax);
+    const float xf = floorf(X0), yf = floorf(Y0);
+    return Origin{static_cast<int>(xf), static_cast<int>(yf), X0 - xf, Y0 - yf};
+}
+__device__ __forceinline__ void write_meta(const LookupParams& p, const Cta& c, const Pending& pd, const Origin& og, Meta& m,
+                                           int lq, bool first_thread) {
+    m.ax[lq] = og.ax;
+    m.ay[lq] = og.ay;
+    m.o[lq] = pd.qid >= 0 ? (og.x0 & 3) : -1;
+    m.out_off[lq] = static_cast<unsigned>((pd.b * (SF_NUM_LEVELS * kSide * kSide) + c.lvl * (kSide * kSide)) * p.N + pd.n);
+    if (first_thread) m.grp = pd.grp;
+}
+
+// stage C, lane = query: conflict-free LDS.128 of its own rows (row pitch kPitch floats), horizontal then vertical lerp in
+// registers, one 128-byte coalesced store per output channel straight into the NCHW result (channel = l*81 + i*9 + j,
+// i moves x, j moves y).  The 9 y-offsets are split 3 + 2 + 2 + 2 over the warps; `ws` says which share this warp takes
+// (the caller rotates it with the item: warp w of every resident CTA shares one scheduler).
+// (8-byte loads + one select per value instead of 16-byte loads + two selects were measured: same time.)
+template <bool kHalfOut, int kPitch, bool kSwz = false>
+__device__ __forceinline__ void stage_c(const LookupParams& p, const Meta& m, const float* winq, int lane, int ws) {
+    const int o = m.o[lane];
+    if (o < 0) return;
+    const int jb = (ws == 0) ? 0 : (2 * ws + 1);           // 0,3,5,7
+    const int je = (ws == 0) ? 2 : (2 * ws + 2);           // 2,4,6,8
+    const float ax = m.ax[lane], ay = m.ay[lane];
+    const float4* wq = reinterpret_cast<const float4*>(winq);
+    // uniform 64-bit base (kernel parameter) + 32-bit per-lane element offset: one IMAD.WIDE per store
+    float* const outf = reinterpret_cast<float*>(p.out[m.grp]);
+    __half* const outh = reinterpret_cast<__half*>(p.out[m.grp]);
+    const unsigned ooff = m.out_off[lane];
+    const unsigned nine_n = static_cast<unsigned>(kSide * p.N), un = static_cast<unsigned>(p.N);
+    float hprev[kSide];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        if (r < jb || r > je + 1) continue;
+        float t[16];
+        {
+            const int x = kSwz ? ((r >> 1) & 3) : 0;    // chunk swizzle of the staged row (see the loader)
+            const float4 c0 = wq[r * (kPitch / 4) + (0 ^ x)], c1 = wq[r * (kPitch / 4) + (1 ^ x)],
+                         c2 = wq[r * (kPitch / 4) + (2 ^ x)], c3 = wq[r * (kPitch / 4) + (3 ^ x)];
+            t[0] = c0.x; t[1] = c0.y; t[2] = c0.z; t[3] = c0.w;
+            t[4] = c1.x; t[5] = c1.y; t[6] = c1.z; t[7] = c1.w;
+            t[8] = c2.x; t[9] = c2.y; t[10] = c2.z; t[11] = c2.w;
+            t[12] = c3.x; t[13] = c3.y; t[14] = c3.z; t[15] = c3.w;
+        }
+        float s1[12], u[10], hcur[kSide];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s1[i] = (o & 1) ? t[i + 1] : t[i];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) u[i] = (o & 2) ? s1[i + 2] : s1[i];
+#pragma unroll
+        for (int i = 0; i < kSide; ++i) hcur[i] = fmaf(ax, u[i + 1] - u[i], u[i]);
+        if (r > jb) {
+            unsigned off = ooff + static_cast<unsigned>(r - 1) * un;      // channel i*9 + j, j = r - 1
+#pragma unroll
+            for (int i = 0; i < kSide; ++i) {
+                const float v = fmaf(ay, hcur[i] - hprev[i], hprev[i]);
+                if (kHalfOut) {
+                    outh[off] = __float2half_rn(v);
+                } else {
+                    __stcs(outf + off, v);
+                }
+                off += nine_n;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kSide; ++i) hprev[i] = hcur[i];
+    }
+}
+
+// ===================================================================================================================
+// Variant 1 (cp.async): windows go global -> shared with 16-byte LDGSTS, double-buffered, 5 CTAs of 43 KB per SM.
+//   A  every thread, thread = (query, row inside a tile): coordinates of item k+2 into registers;
+//   B  the same thread turns the coordinates of item k+1 into the window origin -- redundantly in the 4 lanes of a quad,
+//      one of which leaves the metadata in shared memory for stage C -- and issues the up-to 4x4 tiles under the window
+//      as 16-byte cp.async chunks (ignore-src = zeros outside the image); the lane quad fetches the four rows of ONE
+//      64-byte tile, and only the 10 window rows are staged (row 0 = first window row);
+//   C  item k.
+// Measured (profiles/r2_probes.txt): gather alone 8.6 us + stage C alone 6.2 us + skeleton 2.9 us = the kernel's 17 us:
+// they do not overlap, because LDGSTS writes shared memory once per returned 32-byte SECTOR (ncu: 2.4 M shared wavefronts
+// for 147 k LDGSTS instructions, 5.4x the ideal) on the same MIO pipe stage C's LDS / STG need.
+constexpr int kPitchA = 16;                              // 4 tile columns of 4 floats per staged row
+constexpr int kStrideA = kRows * kPitchA + 4;            // 164 floats: 8 consecutive queries -> distinct bank quads
+constexpr bool kSwzA = true;
+
+// 16-byte async copy, or 16 bytes of zeros when `ignore` (the ignore-src predicate form: the source address is not
+// dereferenced then, so out-of-image tiles need no address clamping).  The L2 evict_last policy keeps the window
+// tiles resident for the next refinement iteration (flow moves by ~1 px; a warm-cache ncu capture shows 27 % fewer
+// DRAM bytes than cold) while the 300 MB softmax stream of the aggregation passes through L2 as evict_first.
+template <bool kViaL1>
+__device__ __forceinline__ void cp_async16_zfill(unsigned dst, const float* src, bool ignore, unsigned long long policy) {
+    if constexpr (kViaL1)       // through L1: the four 16-byte requests of a lane quad merge into one 64-byte L2 request
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+            "cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, p, %3;\n\t}"
+            ::"r"(dst), "l"(src), "r"(static_cast<int>(ignore)), "l"(policy)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+            "cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, p, %3;\n\t}"
+            ::"r"(dst), "l"(src), "r"(static_cast<int>(ignore)), "l"(policy)
+            : "memory");
+}
+
 template <bool kHalfOut, bool kViaL1>
-__global__ void __launch_bounds__(128) corr_lookup_kernel(const __grid_constant__ LookupParams p) {
+__global__ void __launch_bounds__(kThreads) corr_lookup_kernel(const __grid_constant__ LookupParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    float* win0 = smem_f;                                   // [2][kQ * kWinStride]
-    Meta* meta = reinterpret_cast<Meta*>(smem_f + 2 * kQ * kWinStride);   // [2]
+    float* win0 = smem_f;                                   // [2][kQ * kStrideA]
+    Meta* meta = reinterpret_cast<Meta*>(smem_f + 2 * kQ * kStrideA);   // [2]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int lq = tid >> 2, rr = tid & 3;                  // loader role: query of the item, row inside a tile
-    const int items = static_cast<int>(p.items), tiles = static_cast<int>(p.tiles), BN = static_cast<int>(p.BN);
-
-    // item -> (group, query tile, level); levels of one tile are adjacent items (block-uniform, 32-bit math)
-    auto decode = [&](int it, int& grp, int& q0, int& lvl) {
-        lvl = it & 3;
-        const unsigned t = static_cast<unsigned>(it) >> 2;
-        grp = static_cast<int>(t / static_cast<unsigned>(tiles));
-        q0 = static_cast<int>(t - static_cast<unsigned>(grp) * tiles) * kQ;
-    };
-    // stage A: coordinates of this thread's query of an item into registers
-    struct Pending {
-        float cx, cy;
-        int grp, lvl, qid, b, n;
-    };
-    auto load_coords = [&](int it, Pending& pd) {
-        pd.cx = pd.cy = -1e30f;
-        pd.qid = -1;
-        pd.grp = pd.lvl = pd.b = pd.n = 0;
-        if (it < items) {
-            int q0;
-            decode(it, pd.grp, q0, pd.lvl);
-            const int qid = q0 + lq;
-            if (qid < BN) {
-                pd.qid = qid;
-                pd.b = (p.N >= BN) ? 0 : static_cast<int>(static_cast<unsigned>(qid) / static_cast<unsigned>(p.N));
-                pd.n = qid - pd.b * p.N;
-                const float* c = p.coords[pd.grp] + static_cast<long long>(pd.b) * 2 * p.N + pd.n;
-                pd.cx = __ldg(c);
-                pd.cy = __ldg(c + p.N);
-            }
-        }
-    };
+    Cta c;
+    c.init(p);
+    const unsigned win_u32 = static_cast<unsigned>(__cvta_generic_to_shared(win0));
     unsigned long long policy;
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    // stage B: window origin + fractions of the item's level, then the window as 16-byte chunks
-    auto stage_item = [&](int it, int buf, const Pending& pd) {
-        if (it < items) {
-            const int lvl = pd.lvl;
-            const float inv = 1.0f / static_cast<float>(1 << lvl);
-            // Far outside the image every tap is zero; clamping keeps the int conversion defined
-            // (NaN / missing coordinates clamp to the lower bound and yield zeros).
-            const float X0 = fminf(fmaxf(pd.cx * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.wl[lvl] + 8));
-            const float Y0 = fminf(fmaxf(pd.cy * inv - static_cast<float>(SF_RADIUS), -16.f), static_cast<float>(p.hl[lvl] + 8));
-            const float xf = floorf(X0), yf = floorf(Y0);
-            const int x0 = static_cast<int>(xf), y0 = static_cast<int>(yf);
-            const int ox = x0 & 3, oy = y0 & 3;             // window origin inside its first tile
-            if (rr == 0) {
-                Meta& m = meta[buf];
-                m.ax[lq] = X0 - xf;
-                m.ay[lq] = Y0 - yf;
-                m.o[lq] = pd.qid >= 0 ? ox : -1;
-                m.out_off[lq] = static_cast<unsigned>((pd.b * (SF_NUM_LEVELS * kSide * kSide) + lvl * (kSide * kSide)) * p.N + pd.n);
-                if (tid == 0) {
-                    m.grp = pd.grp;
-                    m.lvl = lvl;
-                }
-            }
+
+    // stage B: window origin + fractions, then the window as 16-byte chunks
+    auto stage_item = [&](bool valid, int buf, const Pending& pd) {
+        if (valid) {
+            const Origin og = window_origin(c, pd);
+            const int ox = og.x0 & 3, oy = og.y0 & 3;       // window origin inside its first tile
+            if (rr == 0) write_meta(p, c, pd, og, meta[buf], lq, tid == 0);
             if (pd.qid >= 0) {
-                const int th = p.th[lvl], tw = p.tw[lvl];
-                const float* base = p.lvl[pd.grp][lvl] + static_cast<long long>(pd.qid) * p.img[lvl];
-                const int tx0 = x0 >> 2, ty0 = y0 >> 2;
-                const int ncol = (ox + kRows + 3) >> 2;     // tile columns overlapping window columns ox .. ox+9
-                float* dst = win0 + buf * (kQ * kWinStride) + lq * kWinStride;
+                const int tx0 = og.x0 >> 2, ty0 = og.y0 >> 2;
+                // row rr of tile (ty0, tx0); outside the image the address is never dereferenced (ignore-src)
+                const float* src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid) * c.img + ((ty0 * c.tw + tx0) * 16 + rr * 4);
+                // staged row of (tile row 0, lane row rr): window row rr - oy
+                const unsigned dst = win_u32 + static_cast<unsigned>((buf * (kQ * kStrideA) + lq * kStrideA + (rr - oy) * kPitchA) * 4);
+                const bool c4 = (ox == 3);                   // a fourth tile column only then
+                const unsigned utx = static_cast<unsigned>(tx0), utw = static_cast<unsigned>(c.tw);
+                const bool cok0 = utx < utw, cok1 = utx + 1u < utw, cok2 = utx + 2u < utw, cok3 = utx + 3u < utw;
 #pragma unroll
                 for (int tr = 0; tr < 4; ++tr) {            // tile row; this lane owns row rr of every tile
-                    const int wr = tr * 4 + rr - oy;        // window row staged by this (tile row, lane)
-                    if (wr < 0 || wr >= kRows) continue;
-                    const int ty = ty0 + tr;
-                    const bool rowok = (ty >= 0) && (ty < th);
-                    const float* row = base + (rowok ? (ty * tw + tx0) * 16 + rr * 4 : 0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {           // tile column: constant 64-byte steps from here on
-                        if (j >= ncol) continue;
-                        const bool ok = rowok && (tx0 + j >= 0) && (tx0 + j < tw);
-                        cp_async16_zfill<kViaL1>(dst + wr * kRowFloats + j * 4, ok ? row + j * 16 : base, ok, policy);
-                    }
+                    // window row tr*4 + rr - oy must be one of the 10 staged rows
+                    const bool in_win = tr == 0 ? rr >= oy : tr == 1 ? true : tr == 2 ? rr < oy + 2 : rr + 2 < oy;
+                    if (!in_win) continue;
+                    const bool rbad = static_cast<unsigned>(ty0 + tr) >= static_cast<unsigned>(c.th);
+                    const float* s = src + tr * c.row_step;
+                    const unsigned d = dst + tr * (4 * kPitchA * 4);
+                    // 16-byte chunk j of staged row wr lives at chunk j ^ ((wr >> 1) & 3): the four rows of a tile (one L2
+                    // response) then land in four different bank groups instead of two
+                    const unsigned x = kSwzA ? static_cast<unsigned>(((tr * 4 + rr - oy) >> 1) & 3) * 16u : 0u;
+                    cp_async16_zfill<kViaL1>(d + (0u ^ x), s, rbad || !cok0, policy);
+                    cp_async16_zfill<kViaL1>(d + (16u ^ x), s + 16, rbad || !cok1, policy);
+                    cp_async16_zfill<kViaL1>(d + (32u ^ x), s + 32, rbad || !cok2, policy);
+                    if (c4) cp_async16_zfill<kViaL1>(d + (48u ^ x), s + 48, rbad || !cok3, policy);
                 }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const int first = blockIdx.x, step = gridDim.x;
     Pending pd;
     pdl_launch();
     pdl_wait();
     // prologue: item 0 fully issued, coordinates of item 1 in flight
-    load_coords(first, pd);
-    stage_item(first, 0, pd);
-    load_coords(first + step, pd);
+    load_coords(p, c, lq, pd);
+    stage_item(c.t < c.t_total, 0, pd);
+    c.advance();
+    load_coords(p, c, lq, pd);
 
-    int buf = 0;
-    for (int it = first; it < items; it += step, buf ^= 1) {
-        stage_item(it + step, buf ^ 1, pd);                 // win / meta[buf^1] were last read before the previous barrier
-        load_coords(it + 2 * step, pd);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's chunks of item `it` have landed
+    int buf = 0, k = 0;
+    for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, buf ^= 1, ++k) {
+        stage_item(t + c.tstep < c.t_total, buf ^ 1, pd);   // win / meta[buf^1] were last read before the previous barrier
+        c.advance();
+        load_coords(p, c, lq, pd);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's chunks of item `t` have landed
         __syncthreads();                                    // ... and everybody else's, and meta[buf]
-
-        // stage C: lane = query; warp w owns y-offsets j in [jb, je]
-        // (8-byte loads + one select per value instead of 16-byte loads + two selects were measured: same time --
-        // 17.7 vs 17.4 us -- the kernel is bound by the shared-memory / LSU pipe and the gather, not by issue slots)
-        const Meta& m = meta[buf];
-        const int o = m.o[lane];
-        if (o >= 0) {
-            const int jb = (warp == 0) ? 0 : (2 * warp + 1);       // 0,3,5,7
-            const int je = (warp == 0) ? 2 : (2 * warp + 2);       // 2,4,6,8
-            const float ax = m.ax[lane], ay = m.ay[lane];
-            const float4* wq = reinterpret_cast<const float4*>(win0 + buf * (kQ * kWinStride) + lane * kWinStride);
-            // uniform 64-bit base (kernel parameter) + 32-bit per-lane element offset: one IMAD.WIDE per store
-            float* const outf = reinterpret_cast<float*>(p.out[m.grp]);
-            __half* const outh = reinterpret_cast<__half*>(p.out[m.grp]);
-            const unsigned ooff = m.out_off[lane];
-            const unsigned nine_n = static_cast<unsigned>(kSide * p.N), un = static_cast<unsigned>(p.N);
-            float hprev[kSide];
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-                if (r < jb || r > je + 1) continue;
-                float t[16];
-                {
-                    const float4 c0 = wq[r * 4 + 0], c1 = wq[r * 4 + 1], c2 = wq[r * 4 + 2], c3 = wq[r * 4 + 3];
-                    t[0] = c0.x; t[1] = c0.y; t[2] = c0.z; t[3] = c0.w;
-                    t[4] = c1.x; t[5] = c1.y; t[6] = c1.z; t[7] = c1.w;
-                    t[8] = c2.x; t[9] = c2.y; t[10] = c2.z; t[11] = c2.w;
-                    t[12] = c3.x; t[13] = c3.y; t[14] = c3.z; t[15] = c3.w;
-                }
-                float s1[12], u[10], hcur[kSide];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) s1[i] = (o & 1) ? t[i + 1] : t[i];
-#pragma unroll
-                for (int i = 0; i < 10; ++i) u[i] = (o & 2) ? s1[i + 2] : s1[i];
-#pragma unroll
-                for (int i = 0; i < kSide; ++i) hcur[i] = fmaf(ax, u[i + 1] - u[i], u[i]);
-                if (r > jb) {
-                    unsigned off = ooff + static_cast<unsigned>(r - 1) * un;      // channel i*9 + j, j = r - 1
-#pragma unroll
-                    for (int i = 0; i < kSide; ++i) {
-                        const float v = fmaf(ay, hcur[i] - hprev[i], hprev[i]);
-                        if (kHalfOut) {
-                            outh[off] = __float2half_rn(v);
-                        } else {
-                            __stcs(outf + off, v);
-                        }
-                        off += nine_n;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < kSide; ++i) hprev[i] = hcur[i];
-            }
-        }
+        stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane, (warp + k) & 3);
         __syncthreads();                                    // win[buf] / meta[buf] are rewritten by the next iteration
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-constexpr int kLookupSmem = 2 * kQ * kWinStride * 4 + 2 * static_cast<int>(sizeof(Meta));
+constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof(Meta));
+
+// ===================================================================================================================
+// Variant 2 (register-staged): the window chunks of item k+1 travel global -> REGISTERS (LDG.128, in flight during stage
+// C of item k) -> shared (STS.128, 4 wavefronts per warp instruction instead of one per returned sector), ONE window
+// buffer per CTA.  A loader lane (query, row rr inside a tile) owns at most 3 tile rows x 4 tile columns = 12 chunks.
+// Row pitch 24 floats (96 B) and query stride 244 floats (976 B): the loader's quarter-warp (2 queries x 4 rows) and
+// stage C's quarter-warp (8 queries x 1 row) both hit 8 distinct 16-byte bank groups (6*rr mod 8 = 0,6,4,2; 61*q mod 8 = q).
+constexpr int kPitchB = 24;
+constexpr int kStrideB = kRows * kPitchB + 4;            // 244 floats
+constexpr int kCtasB = 4;                                // <= 128 registers per thread (5 CTAs = 96 registers + spills: 20.2 us)
+
+__device__ __forceinline__ float4 ldg_window16(const float* src, unsigned long long policy) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(src), "l"(policy));
+    return v;
+}
+
+template <bool kHalfOut>
+__global__ void __launch_bounds__(kThreads, kCtasB) corr_lookup_reg_kernel(const __grid_constant__ LookupParams p) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* win = smem_f;                                    // [kQ * kStrideB]
+    Meta* meta = reinterpret_cast<Meta*>(smem_f + kQ * kStrideB);       // [2]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int lq = tid >> 2, rr = tid & 3;                  // loader role: query of the item, row inside a tile
+    Cta c;
+    c.init(p);
+    unsigned long long policy;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+
+    float4 v[3][4];                                         // chunks in flight: tile rows tr0 .. tr0+2, tile columns 0..3
+    int oxy = -1;                                           // (ox | oy << 2) of the item in flight, -1: nothing to store
+
+    // stage B: window origin + fractions -> meta[mb]; the window chunks of the item -> registers
+    auto fetch_item = [&](bool valid, int mb, const Pending& pd) {
+        oxy = -1;
+        if (!valid) return;
+        const Origin og = window_origin(c, pd);
+        const int ox = og.x0 & 3, oy = og.y0 & 3;
+        if (rr == 0) write_meta(p, c, pd, og, meta[mb], lq, tid == 0);
+        if (pd.qid < 0) return;
+        oxy = ox | (oy << 2);
+        const int tx0 = og.x0 >> 2, ty0 = og.y0 >> 2;
+        const int tr0 = rr >= oy ? 0 : 1;                   // first tile row whose row rr lies inside the window
+        const float* src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid) * c.img +
+                           (((ty0 + tr0) * c.tw + tx0) * 16 + rr * 4);
+        const bool c4 = (ox == 3);
+        const unsigned utx = static_cast<unsigned>(tx0), utw = static_cast<unsigned>(c.tw);
+        const bool cok[4] = {utx < utw, utx + 1u < utw, utx + 2u < utw, c4 && utx + 3u < utw};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int wr = (tr0 + i) * 4 + rr - oy;         // >= 0 by the choice of tr0
+            const bool rok = wr < kRows && static_cast<unsigned>(ty0 + tr0 + i) < static_cast<unsigned>(c.th);
+            const float* s = src + i * c.row_step;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[i][j] = (rok && cok[j]) ? ldg_window16(s + j * 16, policy) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // registers -> the window buffer (rows outside the 10-row window and the unused fourth column are skipped)
+    auto store_item = [&]() {
+        if (oxy < 0) return;
+        const int ox = oxy & 3, oy = oxy >> 2;
+        const int tr0 = rr >= oy ? 0 : 1;
+        float4* dst = reinterpret_cast<float4*>(win + lq * kStrideB + (tr0 * 4 + rr - oy) * kPitchB);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if ((tr0 + i) * 4 + rr - oy >= kRows) continue;
+            float4* d = dst + i * (4 * kPitchB / 4);
+            d[0] = v[i][0];
+            d[1] = v[i][1];
+            d[2] = v[i][2];
+            if (ox == 3) d[3] = v[i][3];
+        }
+    };
+
+    Pending pd;
+    pdl_launch();
+    pdl_wait();
+    // prologue: item 0 in flight, coordinates of item 1 in flight
+    load_coords(p, c, lq, pd);
+    fetch_item(c.t < c.t_total, 0, pd);
+    c.advance();
+    load_coords(p, c, lq, pd);
+
+    int k = 0;
+    for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
+        store_item();                                       // item k: registers -> shared (waits for its loads)
+        __syncthreads();                                    // window + meta[k & 1] complete
+        fetch_item(t + c.tstep < c.t_total, (k + 1) & 1, pd);   // item k+1 -> registers, in flight during stage C
+        c.advance();
+        load_coords(p, c, lq, pd);
+        stage_c<kHalfOut, kPitchB>(p, meta[k & 1], win + lane * kStrideB, lane, (warp + k) & 3);
+        __syncthreads();                                    // the window buffer is rewritten by the next iteration
+    }
+}
+
+constexpr int kLookupSmemB = kQ * kStrideB * 4 + 2 * static_cast<int>(sizeof(Meta));
 
 }  // namespace
 
@@ -235,24 +402,36 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
                    p.tiles * groups * SF_NUM_LEVELS < (1ll << 31),
                "corr_lookup: %lld queries per group exceed the 32-bit index range of the kernel", p.BN);
     p.items = p.tiles * groups * SF_NUM_LEVELS;
-    // 5 CTAs of 43 KB per SM, persistent over the work items
-    const int grid = static_cast<int>(std::min<long long>(p.items, 5ll * num_sms));
-    // cp.async.cg (L2 only) by default: measured 17.4 us vs 21.0 us through L1 for the 3-pair launch (the L1 path
-    // wins only when the whole footprint is L2-resident, e.g. a single pair: 7.3 vs 8.1 us); STREAMCORR_LOOKUP_CA=1
-    static const bool via_l1 = [] {
-        const char* e = getenv("STREAMCORR_LOOKUP_CA");
-        return e && e[0] == '1';
+    // Variant: short launches (fewer than two items per resident CTA: one Sintel / KITTI pair, the reference model's
+    // own per-pair calls) are dominated by latency and run the register-staged kernel (6.8 us vs 7.5 us for one Sintel
+    // pair), longer ones the cp.async kernel (16.4 us vs 17.3 us for three pairs).  STREAMCORR_LOOKUP = reg | cpasync
+    // forces one; = ca is cp.async through L1 (measured 21.0 us vs 17.4 us for three pairs).
+    const int forced = [] {                                  // read per launch: the parity tests switch variants
+        const char* e = getenv("STREAMCORR_LOOKUP");
+        if (e && e[0] == 'r') return 1;
+        if (e && e[0] == 'c' && e[1] == 'a') return 2;
+        if (e && e[0] == 'c') return 0;
+        return -1;
     }();
-    auto launch = [&](auto kernel) -> int {
-        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kLookupSmem)) return rc;
+    const int variant = forced >= 0 ? forced : (p.items < 2ll * 5 * num_sms ? 1 : 0);
+    auto launch = [&](auto kernel, int smem, int ctas_per_sm) -> int {
+        // persistent CTAs; a multiple of 4: CTA c works on level c & 3 only (items is a multiple of 4)
+        const int grid = static_cast<int>(std::min<long long>(p.items, static_cast<long long>(ctas_per_sm) * num_sms)) & ~3;
+        if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
         prof_before(SF_KERNEL_LOOKUP, s);
-        SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(128), static_cast<size_t>(kLookupSmem), s, p));
+        SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem), s, p));
         prof_after(SF_KERNEL_LOOKUP, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;
     };
-    if (via_l1) return p.out_f16 ? launch(corr_lookup_kernel<true, true>) : launch(corr_lookup_kernel<false, true>);
-    return p.out_f16 ? launch(corr_lookup_kernel<true, false>) : launch(corr_lookup_kernel<false, false>);
+    if (variant == 1)
+        return p.out_f16 ? launch(corr_lookup_reg_kernel<true>, kLookupSmemB, kCtasB)
+                         : launch(corr_lookup_reg_kernel<false>, kLookupSmemB, kCtasB);
+    if (variant == 2)
+        return p.out_f16 ? launch(corr_lookup_kernel<true, true>, kLookupSmemA, 5)
+                         : launch(corr_lookup_kernel<false, true>, kLookupSmemA, 5);
+    return p.out_f16 ? launch(corr_lookup_kernel<true, false>, kLookupSmemA, 5)
+                     : launch(corr_lookup_kernel<false, false>, kLookupSmemA, 5);
 }
 
 }  // namespace sf

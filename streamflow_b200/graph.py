@@ -65,8 +65,6 @@ class GraphedModel:
     """
 
     def __init__(self, model, frames_shape, iters: int = 12, pad_mode: str = "sintel", warmup: int = 2):
-        import sys
-
         from .corr import coords_grid as device_coords_grid
         from .flowio import InputPadder
 
@@ -80,7 +78,9 @@ class GraphedModel:
         self.model, self.iters, self.device = model, int(iters), dev
         self.frames = torch.zeros((T, C, H, W), dtype=torch.uint8, device=dev)
         padder = InputPadder((H, W), mode=pad_mode)
-        mod = sys.modules.get(model.__class__.__module__)
+        # the module namespace `forward` / `initialize_flow` resolve `coords_grid` in (the model file may have been
+        # executed under any module name, registered in sys.modules or not)
+        ns = getattr(type(model).initialize_flow, "__globals__", None) if hasattr(type(model), "initialize_flow") else None
 
         def dev_grid(batch, ht, wd):
             return device_coords_grid(batch, ht, wd, device=dev)
@@ -90,15 +90,15 @@ class GraphedModel:
             out = model(padder.pad_list(frames), iters=self.iters, test_mode=True)
             return torch.cat([padder.unpad(o) for o in out], 0).contiguous()
 
-        saved = getattr(mod, "coords_grid", None) if mod is not None else None
+        saved = ns.get("coords_grid") if ns is not None else None
         if saved is not None:
-            mod.coords_grid = dev_grid
+            ns["coords_grid"] = dev_grid
         try:
             with torch.cuda.device(dev), torch.no_grad():
                 inner = GraphedCall(fn, warmup=warmup, device=dev)
         finally:
             if saved is not None:
-                mod.coords_grid = saved
+                ns["coords_grid"] = saved
         self._inner = inner
         self.launches = inner.launches
 

@@ -28,9 +28,13 @@ def small():
     return load_golden("corr_small.npz")
 
 
+@pytest.mark.parametrize("variant", ["reg", "cpasync"])
 @pytest.mark.parametrize("name", SETS)
-def test_lookup_on_reference_pyramid(small, name):
+def test_lookup_on_reference_pyramid(small, name, variant, monkeypatch):
+    """Both lookup kernels (register-staged for short launches, cp.async for long ones; the library picks by launch
+    size, STREAMCORR_LOOKUP forces one) against the reference's grid_sample lookup on the reference's own pyramid."""
     from streamflow_b200 import CorrBlock
+    monkeypatch.setenv("STREAMCORR_LOOKUP", variant)
     blk = CorrBlock.from_dense_pyramid([cuda(small[f"level{l}"]) for l in range(4)])
     out = blk(cuda(small[f"coords_{name}"]))
     assert out.shape == (1, 324, 17, 20) and out.dtype == torch.float32 and out.is_contiguous()

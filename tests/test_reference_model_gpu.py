@@ -135,3 +135,33 @@ def test_operators_inside_the_real_caller():
         ours.update_block.aggregator.gamma.zero_()
     c = _run(ours, frames, 2)
     assert _epe(b[0], c[0]) > 1e-5          # and it reaches the flow
+
+
+def test_whole_forward_graph_replay_matches_eager():
+    """streamflow_b200.GraphedModel: the unmodified model's forward on the B200 operators captured once and replayed as ONE
+    CUDA graph returns exactly the eager flows, also for a second clip written into the static input,
+    and leaves the model module's own `coords_grid` in place afterwards."""
+    import streamflow_b200 as sfb
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    H, W, T = 188, 320, 4                                        # 188 rows: exercises the padder inside the graph
+    _, ours, _ = _pair(T, seed=5)
+    ns = type(ours).initialize_flow.__globals__
+    grid_fn = ns["coords_grid"]
+    from streamflow_b200.flowio import InputPadder
+    padder = InputPadder((H, W))
+    clips = [torch.stack([f[0] for f in mh.synthetic_clip(T, H, W, seed=s)]).clamp(0, 255).to(torch.uint8) for s in (1, 2)]
+    gm = sfb.GraphedModel(ours, (T, 3, H, W), iters=12)
+    assert ns["coords_grid"] is grid_fn
+    assert gm.launches >= 12 * (T - 1)
+    for clip in clips:
+        frames = [f[None].float().cuda() for f in clip]
+        eager = torch.cat([padder.unpad(o) for o in _run(ours, padder.pad_list(frames), 12)], 0)
+        replay = gm(clip.cuda())
+        torch.cuda.synchronize()
+        assert replay.shape == (T - 1, 2, H, W)
+        diff = (replay - eager).abs().max().item()      # measured 0.0; cuDNN may pick another algorithm under capture
+        assert diff < 1e-3, f"graph replay differs from the eager forward by {diff} px"
+    with pytest.raises(sfb.StreamCorrError):
+        sfb.GraphedModel(ours.train(), (T, 3, H, W))
+    ours.eval()

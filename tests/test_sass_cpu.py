@@ -63,6 +63,14 @@ def test_lookup_is_a_cp_async_gather(sass):
     assert count(k, "LDGSTS.E.BYPASS.128") >= 16 and count(k, "UTCHMMA") == 0
 
 
+def test_short_lookup_launches_stage_through_registers(sass):
+    """The latency-bound variant (one pair per launch): LDG.128 into registers, STS.128 into ONE window buffer, no
+    cp.async at all, no spills."""
+    k = kernel(sass, "22corr_lookup_reg_kernelILb0E")
+    assert count(k, "LDG.E.NA.128") >= 12 and count(k, "STS.128") >= 9 and count(k, "LDGSTS") == 0
+    assert count(k, "STL") == 0 and count(k, "LDL") == 0
+
+
 def test_correlation_gemm_default_runs_on_cta_pairs(sass):
     """Round 2: the default correlation GEMM is the cta_group::2 kernel (M = 256, B tile shared by the pair)."""
     k = kernel(sass, "21corr_gemm_pair_kernelE")
