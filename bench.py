@@ -575,8 +575,23 @@ def run_ours(args):
                 full_model["upsample_kernel_mean_epe_px_per_pair"] = [
                     float(x) for x in torch.sqrt(((fu - fr) ** 2).sum(1)).mean(dim=(1, 2))]
                 del fu
+                # ... plus the motion encoder's entry: the first stage of its four PCBlocks on
+                # sf_pcblock_ffn1 (streamflow_b200.patch_motion_encoder), eager and as one graph replay of the forward
+                patched = sfb.patch_motion_encoder(our_model)
+                ms_all = _time_events(lambda: runner(frames_host), k_e2e, 2, barrier)
+                fa = runner.flows_on_device(frames_host)
+                gm_all = sfb.GraphedModel(our_model, (T, 3, Hs, Ws), iters=ITERS)
+                ms_all_graph = _time_events(lambda: e2e_host_flows.copy_(gm_all(frames_host), non_blocking=True), k_e2e, 2,
+                                            barrier)
+                full_model["all_patches"] = {
+                    "patched": ["upsample_flow"] + [f"encoder.{n}.ffn1" for n in patched],
+                    "eager_ms": ms_all, "graph_ms": ms_all_graph, "graph_flows_per_s": PAIRS / (ms_all_graph / 1e3),
+                    "speedup_vs_reference_l1": ms_ref / ms_all_graph,
+                    "mean_epe_px_per_pair": [float(x) for x in torch.sqrt(((fa - fr) ** 2).sum(1)).mean(dim=(1, 2))]}
+                del fa, gm_all
             finally:
                 cls.upsample_flow = orig_up
+                sfb.unpatch_motion_encoder(our_model)
             del ref_runner, fo, fr
     else:
         # fallback boundary: the hot-path call chain itself with host buffers (fm uploaded as the fp16 it is)

@@ -83,6 +83,7 @@ SF_API int sf_device_ok(void);
 #define SF_KERNEL_GMA_PROJ 6     /* q/k projection (attention) and the per-iteration fp16 operand cast (aggregate) */
 #define SF_KERNEL_CORR_SIMT 8
 #define SF_KERNEL_UPSAMPLE 9
+#define SF_KERNEL_PCBLOCK_FFN1 10
 SF_API int64_t sf_launch_count(void);
 SF_API void sf_profile_kernel(int which, void* start, void* stop);
 /* Measurement only: restrict the calling thread's sf_gma_aggregate to a subset of its kernels (bit 0 = fp16 operand cast,
@@ -175,6 +176,20 @@ SF_API int sf_gma_aggregate(const void* E, const float* rowsum, const void* fmap
  * flow: [N, 2, H, W] fp32 contiguous; mask: [N, 576, H, W] contiguous of dtype mask_dtype; out: [N, 2, 8H, 8W] fp32. */
 SF_API int sf_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
                      int64_t W, int ratio, void* stream);
+
+/* Motion-encoder entry, SURVEY 8(f) row 2.  Replaces the first line of PCBlock4_Deep_nopool_res.forward
+ * (core/update.py:31, modules built at core/update.py:18-22): `x = F.gelu(x + self.ffn1(x))` with
+ * ffn1 = Conv2d(C, 1.5 C, 1) -> GELU -> Conv2d(1.5 C, C, 1), i.e. per pixel
+ *   out[p, :, n] = gelu(x[p, :, n] + W2 . gelu(W1 . x[p, :, n] + b1) + b2)         (exact-erf GELU)
+ * x, out: [P, C, N] contiguous (N = h * w), dtype fp32 or fp16 (SF_DT_*); fp16 operands, fp32 accumulate.
+ * w1p: fp16 [ceil128(hidden), ceil64(C)] = W1 zero-padded;   b1p: fp32 [ceil128(hidden)] zero-padded;
+ * w2p: fp16 [ceil16(C), ceil128(hidden)] = W2 zero-padded;   b2:  fp32 [C].
+ * Specialised for C <= 384 and hidden <= 512 (convc1: 324 / 486, convc2 and conv: 256 / 384, convf2: 128 / 192). */
+SF_API int sf_pcblock_ffn1(const void* x, int x_dtype, const void* w1p, const float* b1p, const void* w2p, const float* b2,
+                    void* out, int out_dtype, int64_t P, int64_t C, int64_t hidden, int64_t N, void* stream);
+
+/* Debug only: device buffer of 32 x uint64 receiving %globaltimer stamps of one CTA of sf_pcblock_ffn1 (NULL = off). */
+SF_API void sf_debug_ffn1_trace(void* dev_ptr);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,9 @@ from .corr import CorrBlock, CorrGroup, coords_grid  # noqa: F401
 from .gma import Aggregate, Attention, AttentionHandle  # noqa: F401
 from .graph import GraphedCall, GraphedModel  # noqa: F401
 from .install import install, uninstall  # noqa: F401
+from .pcblock import patch_motion_encoder, pcblock_ffn1, unpatch_motion_encoder  # noqa: F401
 from .upsample import patch_upsample, upsample_flow  # noqa: F401
 
 __all__ = ["CorrBlock", "CorrGroup", "coords_grid", "Attention", "Aggregate", "AttentionHandle", "install",
-           "uninstall", "upsample_flow", "patch_upsample", "StreamCorrError", "lib", "GraphedCall", "GraphedModel"]
+           "uninstall", "upsample_flow", "patch_upsample", "StreamCorrError", "lib", "GraphedCall", "GraphedModel",
+           "pcblock_ffn1", "patch_motion_encoder", "unpatch_motion_encoder"]

@@ -28,7 +28,7 @@ EXPORTS = [
     "sf_debug_select_kernels", "sf_corr_level_dims", "sf_corr_workspace_bytes",
     "sf_corr_build", "sf_corr_lookup", "sf_corr_lookup_group", "sf_gma_npad", "sf_gma_e_elems",
     "sf_gma_workspace_bytes",
-    "sf_gma_attention", "sf_gma_attention_qk", "sf_gma_aggregate", "sf_upsample_flow",
+    "sf_gma_attention", "sf_gma_attention_qk", "sf_gma_aggregate", "sf_upsample_flow", "sf_pcblock_ffn1", "sf_debug_ffn1_trace",
 ]
 
 _lib = None
@@ -86,6 +86,11 @@ def lib() -> ctypes.CDLL:
     L.sf_gma_aggregate.restype = c_int
     L.sf_upsample_flow.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]
     L.sf_upsample_flow.restype = c_int
+    L.sf_pcblock_ffn1.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64,
+                                  c_int64, c_int64, c_int64, c_void_p]
+    L.sf_pcblock_ffn1.restype = c_int
+    L.sf_debug_ffn1_trace.argtypes = [c_void_p]
+    L.sf_debug_ffn1_trace.restype = None
     _lib = L
     return L
 

@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "..", "build", "obj")
 LIB = os.path.join(HERE, "libstreamcorr.so")
 
 SOURCES = ["api.cu", "gma_api.cu", "corr_lookup.cu", "corr_pack.cu", "corr_simt.cu", "corr_gemm_sm100.cu",
-           "gma_sm100.cu", "gma_aggregate_sm100.cu", "gma_proj.cu", "upsample.cu"]
+           "gma_sm100.cu", "gma_aggregate_sm100.cu", "gma_proj.cu", "upsample.cu", "pcblock_ffn1_sm100.cu"]
 HEADERS = ["sf_internal.h", "sm100_ptx.cuh", os.path.join("..", "..", "include", "streamcorr.h")]
 
 NVCC_FLAGS = [

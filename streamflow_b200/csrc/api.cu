@@ -137,7 +137,7 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, bool swizzle128) {
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, int swizzle_bytes) {
     // A tensor map is a pure function of its arguments (the driver call costs ~1-2 us, and a step re-encodes the
     // same ~10 maps for every clip of a stream): small per-thread direct-mapped cache keyed by all of them.
     struct Entry {
@@ -148,7 +148,7 @@ int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_
     constexpr int kSlots = 64;
     static thread_local Entry cache[kSlots];
     const uint64_t key[9] = {static_cast<uint64_t>(dt), reinterpret_cast<uint64_t>(base), d0, d1, d2, stride1, stride2,
-                             (static_cast<uint64_t>(b0) << 32) | b1, static_cast<uint64_t>(swizzle128)};
+                             (static_cast<uint64_t>(b0) << 32) | b1, static_cast<uint64_t>(swizzle_bytes)};
     uint64_t hsh = 1469598103934665603ull;
     for (uint64_t k : key) hsh = (hsh ^ k) * 1099511628211ull;
     Entry& e = cache[(hsh >> 17) % kSlots];
@@ -166,7 +166,7 @@ int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_
     const cuuint32_t box[3] = {b0, b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = fn(m, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -401,6 +401,21 @@ int sf_corr_lookup(const float* const levels[SF_NUM_LEVELS], const float* coords
 int sf_corr_lookup_group(int G, const float* const* levels, const float* const* coords, void* const* out,
                          int out_dtype, int64_t B, int64_t h, int64_t w, int radius, int num_levels, void* stream) {
     return lookup_common(G, levels, coords, out, out_dtype, B, h, w, radius, num_levels, stream);
+}
+
+void sf_debug_ffn1_trace(void* dev_ptr) { set_ffn1_trace(dev_ptr); }
+
+int sf_pcblock_ffn1(const void* x, int x_dtype, const void* w1p, const float* b1p, const void* w2p, const float* b2,
+                    void* out, int out_dtype, int64_t P, int64_t C, int64_t hidden, int64_t N, void* stream) {
+    DeviceInfo di;
+    if (int rc = query_device(&di)) return rc;
+    SF_REQUIRE(x && w1p && b1p && w2p && b2 && out, "pcblock_ffn1: null pointer argument");
+    SF_REQUIRE((x_dtype == SF_DT_F32 || x_dtype == SF_DT_F16) && (out_dtype == SF_DT_F32 || out_dtype == SF_DT_F16),
+               "pcblock_ffn1: x / out must be fp32 or fp16 (got dtype codes %d, %d)", x_dtype, out_dtype);
+    SF_REQUIRE(((reinterpret_cast<uintptr_t>(w1p) | reinterpret_cast<uintptr_t>(w2p) | reinterpret_cast<uintptr_t>(b1p)) & 15) == 0,
+               "pcblock_ffn1: packed weights must be 16-byte aligned");
+    return launch_pcblock_ffn1(x, x_dtype, w1p, b1p, w2p, b2, out, out_dtype, P, C, hidden, N,
+                               static_cast<cudaStream_t>(stream));
 }
 
 int sf_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H, int64_t W,

@@ -102,9 +102,9 @@ struct DeviceInfo {
 int ensure_dynamic_smem(const void* func, int bytes);
 // SF_OK and fills `out` when the current device is sm_100; SF_ERR_NODEVICE (with message) otherwise.
 int query_device(DeviceInfo* out);
-// rank-3 tiled TMA map, 128B swizzle: dims / box innermost first; strides (bytes) of dims 1 and 2; box[2] = 1.
+// rank-3 tiled TMA map (128-byte swizzle by default; 64 or 0 = none): dims / box innermost first; strides (bytes) of dims 1 and 2; box[2] = 1.
 int make_tmap3(CUtensorMap* m, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
-               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, bool swizzle128 = true);
+               uint64_t stride1, uint64_t stride2, uint32_t b0, uint32_t b1, const char* what, int swizzle_bytes = 128);
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // Power-of-two operand scale derived from a tensor's absmax (bits of a non-negative float):
@@ -229,6 +229,12 @@ struct GmaAggParams {
 int launch_gma_aggregate(const GmaAggParams& p, const CUtensorMap& tm_x, const CUtensorMap& tm_w, int num_sms,
                          unsigned* settled, cudaStream_t s);
 int launch_gma_identity(float* dst, int d, cudaStream_t s);      // dst[d, d] <- I
+
+// y = gelu(x + W2 . gelu(W1 . x + b1) + b2) per pixel (pcblock_ffn1_sm100.cu); w1p [Hp, Kp], w2p [ceil16(C), Hp] fp16 padded (Hp = ceil128(hidden), Kp = ceil64(C))
+int launch_pcblock_ffn1(const void* x, int x_dtype, const void* w1p, const float* b1p, const void* w2p, const float* b2,
+                        void* out, int out_dtype, int64_t P, int64_t C, int64_t Hd, int64_t N, cudaStream_t s);
+
+void set_ffn1_trace(void* dev_ptr);     // debug: 32 x u64 of %globaltimer stamps (see pcblock_ffn1_sm100.cu)
 
 int launch_upsample_flow(const float* flow, const void* mask, int mask_dtype, float* out, int64_t N, int64_t H,
                          int64_t W, cudaStream_t s);

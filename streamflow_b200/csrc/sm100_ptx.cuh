@@ -244,6 +244,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// Same for rows of 64 B with the 64-byte swizzle (TMA box {32 x fp16, rows}, CU_TENSOR_MAP_SWIZZLE_64B):
+// SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B = 4.
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate (c_format 1), both K-major.
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int m, int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | (static_cast<uint32_t>(n >> 3) << 17) |

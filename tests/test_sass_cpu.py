@@ -71,6 +71,14 @@ def test_short_lookup_launches_stage_through_registers(sass):
     assert count(k, "STL") == 0 and count(k, "LDL") == 0
 
 
+def test_motion_encoder_entry_is_a_two_gemm_tcgen05_kernel(sass):
+    """sf_pcblock_ffn1: both 1x1 convolutions on tcgen05 (4 + 4 MMA issue sites), weights by TMA, accumulators read back with
+    tcgen05.ld, GELU via one MUFU.RCP, no issue waterfall, no spills."""
+    k = kernel(sass, "19pcblock_ffn1_kernelIffE")
+    assert count(k, "UTCHMMA") >= 8 and count(k, "UTMALDG") >= 3 and count(k, "LDTM") >= 3 and count(k, "MUFU.RCP") >= 16
+    assert count(k, "BRA.U.ANY") == 0 and count(k, "STL") == 0 and count(k, "LDL") == 0
+
+
 def test_correlation_gemm_default_runs_on_cta_pairs(sass):
     """Round 2: the default correlation GEMM is the cta_group::2 kernel (M = 256, B tile shared by the pair)."""
     k = kernel(sass, "21corr_gemm_pair_kernelE")
