@@ -757,6 +757,32 @@ def run_ours(args):
         for name, kind in (("gma_stats_pass2", _lib.KERNEL_GMA_STATS), ("corr_pack", _lib.KERNEL_CORR_PACK)):
             us, n = kernel_time(kind)
             kernels[name] = {"us_per_launch_event_pairs_in_step": us, "launches_timed": n}
+        # the motion encoder's entry on the lookup output (convc1: 324 -> 486 -> 324, fp32 in / out),
+        # one launch for the 3 maps of the clip, against the reference's own four eager ops under autocast
+        import torch.nn as nn
+        import torch.nn.functional as F
+        g = torch.Generator().manual_seed(7)
+        ffn1 = nn.Sequential(nn.Conv2d(324, 486, 1), nn.GELU(), nn.Conv2d(486, 324, 1)).to(dev).eval()
+        xin = feats.reshape(PAIRS, 324, H8, W8).clone()
+        us_ffn = graph_kernel_time(lambda i: sfb.pcblock_ffn1(xin, ffn1), ITERS)
+
+        def ref_ffn():
+            with torch.autocast("cuda", dtype=torch.float16):
+                return F.gelu(xin + ffn1(xin))
+        ref_y = F.gelu(xin + ffn1(xin))
+        ffn_rel = _rel(sfb.pcblock_ffn1(xin, ffn1), ref_y)
+        us_ref_ffn = _time_events(ref_ffn, 20, 5, lambda: torch.cuda.synchronize()) * 1e3
+        fl = 2.0 * PAIRS * N * 324 * 486 * 2
+        kernels["pcblock_ffn1"] = {"us_per_launch": us_ffn, "reference_ops_us": us_ref_ffn, "speedup": us_ref_ffn / us_ffn,
+                                   "rel_err_vs_fp32_ops": ffn_rel, "algorithmic_flops": fl,
+                                   "tensor_tflops": fl / us_ffn / 1e6, "tensor_frac": fl / us_ffn / 1e6 / peak_tf,
+                                   "note": "gelu(x + W2 gelu(W1 x + b1) + b2) on the 324-channel lookup output of the clip "
+                                           "(core/update.py:31); bound by the 128 x (512 + 336) exact-erf GELUs per 128-pixel tile "
+                                           "on the FP32 pipe and by shared-memory-operand MMAs, not by the tensor pipe; the "
+                                           "reference runs conv1x1, GELU, conv1x1, add + GELU eagerly under autocast"}
+        if not ffn_rel < 2e-3:
+            raise SystemExit(f"bench.py: pcblock_ffn1 differs from the torch ops by {ffn_rel}")
+        del ffn1, xin, ref_y
         torch.cuda.empty_cache()
 
     # ---- the reference's torch ops on the SAME GPU (like-for-like bar), rank 0 at N=1

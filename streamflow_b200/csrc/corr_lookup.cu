@@ -8,18 +8,16 @@
 // arbitrary offset touches on average 3.25 x 3.25 tiles = 676 B of 64-byte DRAM fetches, against 1024 B for a
 // row-major image (10 rows x 1.6 blocks; measured 87.7 MB of DRAM reads for 33.8 MB of window bytes).
 //
-// Work item = 32 consecutive queries x ONE pyramid level; persistent CTAs (5 per SM) run a software pipeline with TWO
-// block-wide barriers per item and no single-warp phase (an ncu capture of the previous three-barrier version, where
-// warp 0 alone prepared the item's metadata, showed `barrier` as the top stall reason at 41 % issue utilisation):
-//   A  every thread, thread = (query, row inside a tile): coordinates of item k+2 into registers;
-//   B  the same thread turns the coordinates of item k+1 into the integer window origin (x0, y0) and the single
-//      fractional pair (ax, ay) shared by all 81 taps of the level (window offsets are integers) -- redundantly in the 4
-//      lanes of a quad, one of which leaves them in shared memory for stage C -- and issues the up-to 4x4 tiles under
-//      the window as 16-byte cp.async chunks (zero-filled outside the image); the lane quad fetches the four rows of
-//      ONE 64-byte tile, and only the 10 window rows are staged (row 0 = first window row);
-//   C  item k, lane = query: conflict-free LDS.128 of its own rows, horizontal then vertical lerp in registers, and
-//      one 128-byte coalesced store per output channel straight into the NCHW result
-//      (channel = l*81 + i*9 + j, i moves x, j moves y).  Warps split the 9 y-offsets.
+// Work item = 32 consecutive queries x ONE pyramid level, persistent CTAs; per item
+//   A  coordinates of the item after next into registers (loader thread = (query, row inside a tile));
+//   B  the loader turns coordinates into the integer window origin (x0, y0) and the single fractional pair (ax, ay) shared
+//      by all 81 taps of the level (window offsets are integers) -- redundantly in the 4 lanes of a quad, one of which
+//      leaves them in shared memory for stage C -- and fetches the up-to 4x4 tiles under the window as 16-byte chunks
+//      (zeros outside the image); the lane quad fetches the four rows of ONE 64-byte tile, only the 10 window rows are staged;
+//   C  lane = query: conflict-free LDS.128 of its own rows, horizontal then vertical lerp in registers, one 128-byte
+//      coalesced store per output channel straight into the NCHW result (channel = l*81 + i*9 + j, i moves x, j moves y).
+// Two kernels share these stages: a warp-specialised cp.async kernel for long launches and a register-staged one for short
+// launches (see launch_corr_lookup).
 #include <algorithm>
 #include <cstdlib>
 
@@ -181,118 +179,151 @@ __device__ __forceinline__ void stage_c(const LookupParams& p, const Meta& m, co
 }
 
 // ===================================================================================================================
-// Variant 1 (cp.async): windows go global -> shared with 16-byte LDGSTS, double-buffered, 5 CTAs of 43 KB per SM.
-//   A  every thread, thread = (query, row inside a tile): coordinates of item k+2 into registers;
-//   B  the same thread turns the coordinates of item k+1 into the window origin -- redundantly in the 4 lanes of a quad,
-//      one of which leaves the metadata in shared memory for stage C -- and issues the up-to 4x4 tiles under the window
-//      as 16-byte cp.async chunks (ignore-src = zeros outside the image); the lane quad fetches the four rows of ONE
-//      64-byte tile, and only the 10 window rows are staged (row 0 = first window row);
-//   C  item k.
-// Measured (profiles/r2_probes.txt): gather alone 8.6 us + stage C alone 6.2 us + skeleton 2.9 us = the kernel's 17 us:
-// they do not overlap, because LDGSTS writes shared memory once per returned 32-byte SECTOR (ncu: 2.4 M shared wavefronts
-// for 147 k LDGSTS instructions, 5.4x the ideal) on the same MIO pipe stage C's LDS / STG need.
+// Staging layout of the cp.async kernel: per query 10 window rows of 16 floats (4 tile columns), two buffers of 32 queries.
+// History (profiles/r2_probes.txt): with loaders and interpolation in the SAME threads and two block-wide barriers per item
+// the gather (8.6 us alone) and stage C (6.2 us alone) did not overlap at all (17.1 us); leaner loader code, a rotated heavy
+// row share and the bank swizzle below brought that kernel to 16.4 us, warp specialisation (next) to 16.0 us.
 constexpr int kPitchA = 16;                              // 4 tile columns of 4 floats per staged row
 constexpr int kStrideA = kRows * kPitchA + 4;            // 164 floats: 8 consecutive queries -> distinct bank quads
-constexpr bool kSwzA = true;
+constexpr bool kSwzA = true;                             // 16-byte chunk j of staged row wr lives at chunk j ^ ((wr >> 1) & 3): the four
+                                                         // rows of a tile (one L2 response) land in four different bank groups
 
 // 16-byte async copy, or 16 bytes of zeros when `ignore` (the ignore-src predicate form: the source address is not
 // dereferenced then, so out-of-image tiles need no address clamping).  The L2 evict_last policy keeps the window
 // tiles resident for the next refinement iteration (flow moves by ~1 px; a warm-cache ncu capture shows 27 % fewer
 // DRAM bytes than cold) while the 300 MB softmax stream of the aggregation passes through L2 as evict_first.
-template <bool kViaL1>
 __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const float* src, bool ignore, unsigned long long policy) {
-    if constexpr (kViaL1)       // through L1: the four 16-byte requests of a lane quad merge into one 64-byte L2 request
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
-            "cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, p, %3;\n\t}"
-            ::"r"(dst), "l"(src), "r"(static_cast<int>(ignore)), "l"(policy)
-            : "memory");
-    else
-        asm volatile(
+    // .cg (L2 only): through L1 (.ca) the 3-pair launch took 21.0 us against 17.4 us
+    asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
             "cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, p, %3;\n\t}"
             ::"r"(dst), "l"(src), "r"(static_cast<int>(ignore)), "l"(policy)
             : "memory");
 }
 
-template <bool kHalfOut, bool kViaL1>
-__global__ void __launch_bounds__(kThreads) corr_lookup_kernel(const __grid_constant__ LookupParams p) {
+constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof(Meta));
+
+// ===================================================================================================================
+// Kernel 1 (long launches, warp-specialised cp.async): stage A/B runs in two LOADER warps and stage C in four COMPUTE warps, coupled by mbarriers (full[buf]: the loaders' cp.async groups + metadata have landed;
+// empty[buf]: the compute warps are done with the buffer) instead of two block-wide barriers per item.  A loader thread
+// owns row rr of the tiles of TWO queries (lq and lq + 16).  The compute warps never execute loader instructions, and the
+// loaders run up to two items ahead.
+constexpr int kThreadsW = 192;
+
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <bool kHalfOut>
+__global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __grid_constant__ LookupParams p) {
     extern __shared__ __align__(16) float smem_f[];
     float* win0 = smem_f;                                   // [2][kQ * kStrideA]
     Meta* meta = reinterpret_cast<Meta*>(smem_f + 2 * kQ * kStrideA);   // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(meta + 2);  // [2]
+    uint64_t* empty = full + 2;                              // [2]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int lq = tid >> 2, rr = tid & 3;                  // loader role: query of the item, row inside a tile
     Cta c;
     c.init(p);
-    const unsigned win_u32 = static_cast<unsigned>(__cvta_generic_to_shared(win0));
-    unsigned long long policy;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-
-    // stage B: window origin + fractions, then the window as 16-byte chunks
-    auto stage_item = [&](bool valid, int buf, const Pending& pd) {
-        if (valid) {
-            const Origin og = window_origin(c, pd);
-            const int ox = og.x0 & 3, oy = og.y0 & 3;       // window origin inside its first tile
-            if (rr == 0) write_meta(p, c, pd, og, meta[buf], lq, tid == 0);
-            if (pd.qid >= 0) {
-                const int tx0 = og.x0 >> 2, ty0 = og.y0 >> 2;
-                // row rr of tile (ty0, tx0); outside the image the address is never dereferenced (ignore-src)
-                const float* src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid) * c.img + ((ty0 * c.tw + tx0) * 16 + rr * 4);
-                // staged row of (tile row 0, lane row rr): window row rr - oy
-                const unsigned dst = win_u32 + static_cast<unsigned>((buf * (kQ * kStrideA) + lq * kStrideA + (rr - oy) * kPitchA) * 4);
-                const bool c4 = (ox == 3);                   // a fourth tile column only then
-                const unsigned utx = static_cast<unsigned>(tx0), utw = static_cast<unsigned>(c.tw);
-                const bool cok0 = utx < utw, cok1 = utx + 1u < utw, cok2 = utx + 2u < utw, cok3 = utx + 3u < utw;
-#pragma unroll
-                for (int tr = 0; tr < 4; ++tr) {            // tile row; this lane owns row rr of every tile
-                    // window row tr*4 + rr - oy must be one of the 10 staged rows
-                    const bool in_win = tr == 0 ? rr >= oy : tr == 1 ? true : tr == 2 ? rr < oy + 2 : rr + 2 < oy;
-                    if (!in_win) continue;
-                    const bool rbad = static_cast<unsigned>(ty0 + tr) >= static_cast<unsigned>(c.th);
-                    const float* s = src + tr * c.row_step;
-                    const unsigned d = dst + tr * (4 * kPitchA * 4);
-                    // 16-byte chunk j of staged row wr lives at chunk j ^ ((wr >> 1) & 3): the four rows of a tile (one L2
-                    // response) then land in four different bank groups instead of two
-                    const unsigned x = kSwzA ? static_cast<unsigned>(((tr * 4 + rr - oy) >> 1) & 3) * 16u : 0u;
-                    cp_async16_zfill<kViaL1>(d + (0u ^ x), s, rbad || !cok0, policy);
-                    cp_async16_zfill<kViaL1>(d + (16u ^ x), s + 16, rbad || !cok1, policy);
-                    cp_async16_zfill<kViaL1>(d + (32u ^ x), s + 32, rbad || !cok2, policy);
-                    if (c4) cp_async16_zfill<kViaL1>(d + (48u ^ x), s + 48, rbad || !cok3, policy);
-                }
-            }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init_(&full[i], 128);      // per loader thread: one arrival of its cp.async group + one after its metadata
+            mbar_init_(&empty[i], 4);       // one per compute warp
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    Pending pd;
-    pdl_launch();
-    pdl_wait();
-    // prologue: item 0 fully issued, coordinates of item 1 in flight
-    load_coords(p, c, lq, pd);
-    stage_item(c.t < c.t_total, 0, pd);
-    c.advance();
-    load_coords(p, c, lq, pd);
-
-    int buf = 0, k = 0;
-    for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, buf ^= 1, ++k) {
-        stage_item(t + c.tstep < c.t_total, buf ^ 1, pd);   // win / meta[buf^1] were last read before the previous barrier
-        c.advance();
-        load_coords(p, c, lq, pd);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's chunks of item `t` have landed
-        __syncthreads();                                    // ... and everybody else's, and meta[buf]
-        stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane, (warp + k) & 3);
-        __syncthreads();                                    // win[buf] / meta[buf] are rewritten by the next iteration
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    pdl_launch();
+    __syncthreads();
+    pdl_wait();
+
+    if (warp >= 4) {
+        // ------------------------------------------------------------------ loaders
+        const int lt = tid - 128;
+        const int lq0 = lt >> 2, rr = lt & 3;
+        const unsigned win_u32 = static_cast<unsigned>(__cvta_generic_to_shared(win0));
+        unsigned long long policy;
+        asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+        auto stage_query = [&](int buf, int lq, const Pending& pd) {
+            const Origin og = window_origin(c, pd);
+            const int ox = og.x0 & 3, oy = og.y0 & 3;
+            if (rr == 0) write_meta(p, c, pd, og, meta[buf], lq, lq == 0);
+            if (pd.qid < 0) return;
+            const int tx0 = og.x0 >> 2, ty0 = og.y0 >> 2;
+            const float* src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid) * c.img + ((ty0 * c.tw + tx0) * 16 + rr * 4);
+            const unsigned dst = win_u32 + static_cast<unsigned>((buf * (kQ * kStrideA) + lq * kStrideA + (rr - oy) * kPitchA) * 4);
+            const bool c4 = (ox == 3);
+            const unsigned utx = static_cast<unsigned>(tx0), utw = static_cast<unsigned>(c.tw);
+            const bool cok0 = utx < utw, cok1 = utx + 1u < utw, cok2 = utx + 2u < utw, cok3 = utx + 3u < utw;
+#pragma unroll
+            for (int tr = 0; tr < 4; ++tr) {
+                const bool in_win = tr == 0 ? rr >= oy : tr == 1 ? true : tr == 2 ? rr < oy + 2 : rr + 2 < oy;
+                if (!in_win) continue;
+                const bool rbad = static_cast<unsigned>(ty0 + tr) >= static_cast<unsigned>(c.th);
+                const float* s = src + tr * c.row_step;
+                const unsigned d = dst + tr * (4 * kPitchA * 4);
+                const unsigned x = kSwzA ? static_cast<unsigned>(((tr * 4 + rr - oy) >> 1) & 3) * 16u : 0u;
+                cp_async16_zfill(d + (0u ^ x), s, rbad || !cok0, policy);
+                cp_async16_zfill(d + (16u ^ x), s + 16, rbad || !cok1, policy);
+                cp_async16_zfill(d + (32u ^ x), s + 32, rbad || !cok2, policy);
+                if (c4) cp_async16_zfill(d + (48u ^ x), s + 48, rbad || !cok3, policy);
+            }
+        };
+        Pending pa, pb;
+        load_coords(p, c, lq0, pa);
+        load_coords(p, c, lq0 + 16, pb);
+        int k = 0;
+        for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
+            const int buf = k & 1;
+            const Pending qa = pa, qb = pb;
+            c.advance();
+            load_coords(p, c, lq0, pa);                     // coordinates of the next item: in flight during this one
+            load_coords(p, c, lq0 + 16, pb);
+            mbar_wait_(&empty[buf], ((k >> 1) & 1) ^ 1);    // the compute warps are done with item k-2
+            stage_query(buf, lq0, qa);
+            stage_query(buf, lq0 + 16, qb);
+            cp_async_mbar_arrive(&full[buf]);               // fires when this thread's chunks have landed
+            mbar_arrive_(&full[buf]);                       // metadata written (release)
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        // ------------------------------------------------------------------ compute: lane = query
+        int k = 0;
+        for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
+            const int buf = k & 1;
+            mbar_wait_(&full[buf], (k >> 1) & 1);
+            stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane, (warp + k) & 3);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&empty[buf]);
+        }
+    }
 }
 
-constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof(Meta));
+constexpr int kLookupSmemW = kLookupSmemA + 64;
 
 // ===================================================================================================================
-// Variant 2 (register-staged): the window chunks of item k+1 travel global -> REGISTERS (LDG.128, in flight during stage
+// Kernel 2 (short launches, register-staged): the window chunks of item k+1 travel global -> REGISTERS (LDG.128, in flight during stage
 // C of item k) -> shared (STS.128, 4 wavefronts per warp instruction instead of one per returned sector), ONE window
 // buffer per CTA.  A loader lane (query, row rr inside a tile) owns at most 3 tile rows x 4 tile columns = 12 chunks.
 // Row pitch 24 floats (96 B) and query stride 244 floats (976 B): the loader's quarter-warp (2 queries x 4 rows) and
@@ -402,36 +433,31 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
                    p.tiles * groups * SF_NUM_LEVELS < (1ll << 31),
                "corr_lookup: %lld queries per group exceed the 32-bit index range of the kernel", p.BN);
     p.items = p.tiles * groups * SF_NUM_LEVELS;
-    // Variant: short launches (fewer than two items per resident CTA: one Sintel / KITTI pair, the reference model's
-    // own per-pair calls) are dominated by latency and run the register-staged kernel (6.8 us vs 7.5 us for one Sintel
-    // pair), longer ones the cp.async kernel (16.4 us vs 17.3 us for three pairs).  STREAMCORR_LOOKUP = reg | cpasync
-    // forces one; = ca is cp.async through L1 (measured 21.0 us vs 17.4 us for three pairs).
-    const int forced = [] {                                  // read per launch: the parity tests switch variants
+    // Short launches (fewer than two items per resident CTA: one Sintel / KITTI pair, the reference model's own per-pair
+    // calls) are dominated by latency and run the register-staged kernel (6.8 us vs 7.4 us for one Sintel pair), longer ones
+    // the warp-specialised cp.async kernel (16.0 us vs 17.3 us for three pairs).  STREAMCORR_LOOKUP = reg | ws forces one.
+    const int forced = [] {                                  // read per launch: the parity tests switch kernels
         const char* e = getenv("STREAMCORR_LOOKUP");
         if (e && e[0] == 'r') return 1;
-        if (e && e[0] == 'c' && e[1] == 'a') return 2;
-        if (e && e[0] == 'c') return 0;
+        if (e && e[0] == 'w') return 0;
         return -1;
     }();
     const int variant = forced >= 0 ? forced : (p.items < 2ll * 5 * num_sms ? 1 : 0);
-    auto launch = [&](auto kernel, int smem, int ctas_per_sm) -> int {
+    auto launch = [&](auto kernel, int threads, int smem, int ctas_per_sm) -> int {
         // persistent CTAs; a multiple of 4: CTA c works on level c & 3 only (items is a multiple of 4)
         const int grid = static_cast<int>(std::min<long long>(p.items, static_cast<long long>(ctas_per_sm) * num_sms)) & ~3;
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
         prof_before(SF_KERNEL_LOOKUP, s);
-        SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(kThreads), static_cast<size_t>(smem), s, p));
+        SF_CUDA_CHECK(launch_kernel(kernel, dim3(grid), dim3(threads), static_cast<size_t>(smem), s, p));
         prof_after(SF_KERNEL_LOOKUP, s);
         SF_CUDA_CHECK(cudaGetLastError());
         return SF_OK;
     };
     if (variant == 1)
-        return p.out_f16 ? launch(corr_lookup_reg_kernel<true>, kLookupSmemB, kCtasB)
-                         : launch(corr_lookup_reg_kernel<false>, kLookupSmemB, kCtasB);
-    if (variant == 2)
-        return p.out_f16 ? launch(corr_lookup_kernel<true, true>, kLookupSmemA, 5)
-                         : launch(corr_lookup_kernel<false, true>, kLookupSmemA, 5);
-    return p.out_f16 ? launch(corr_lookup_kernel<true, false>, kLookupSmemA, 5)
-                     : launch(corr_lookup_kernel<false, false>, kLookupSmemA, 5);
+        return p.out_f16 ? launch(corr_lookup_reg_kernel<true>, kThreads, kLookupSmemB, kCtasB)
+                         : launch(corr_lookup_reg_kernel<false>, kThreads, kLookupSmemB, kCtasB);
+    return p.out_f16 ? launch(corr_lookup_ws_kernel<true>, kThreadsW, kLookupSmemW, 5)
+                     : launch(corr_lookup_ws_kernel<false>, kThreadsW, kLookupSmemW, 5);
 }
 
 }  // namespace sf

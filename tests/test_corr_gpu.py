@@ -28,10 +28,10 @@ def small():
     return load_golden("corr_small.npz")
 
 
-@pytest.mark.parametrize("variant", ["reg", "cpasync"])
+@pytest.mark.parametrize("variant", ["reg", "ws"])
 @pytest.mark.parametrize("name", SETS)
 def test_lookup_on_reference_pyramid(small, name, variant, monkeypatch):
-    """Both lookup kernels (register-staged for short launches, cp.async for long ones; the library picks by launch
+    """Both lookup kernels (register-staged for short launches, warp-specialised cp.async for long ones; the library picks by launch
     size, STREAMCORR_LOOKUP forces one) against the reference's grid_sample lookup on the reference's own pyramid."""
     from streamflow_b200 import CorrBlock
     monkeypatch.setenv("STREAMCORR_LOOKUP", variant)

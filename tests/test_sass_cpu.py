@@ -58,9 +58,13 @@ def test_aggregate_streams_with_bulk_copies_and_tcgen05(sass):
     assert count(k, "RED.E") == 0 and count(k, "ATOMG") == 0         # no global reduction / atomic: split-K is gone
 
 
-def test_lookup_is_a_cp_async_gather(sass):
-    k = kernel(sass, "18corr_lookup_kernelILb0E")
+def test_lookup_is_a_warp_specialised_cp_async_gather(sass):
+    """Loader warps (LDGSTS + mbarrier arrivals) and interpolation warps coupled by mbarriers: one block-wide barrier at
+    start-up, none per work item."""
+    k = kernel(sass, "21corr_lookup_ws_kernelILb0E")
     assert count(k, "LDGSTS.E.BYPASS.128") >= 16 and count(k, "UTCHMMA") == 0
+    assert count(k, "SYNCS.PHASECHK") >= 2 and count(k, "BAR.SYNC") <= 1 and count(k, "STL") == 0
+    assert not any("18corr_lookup_kernel" in name for name in sass)      # the two-barrier kernel is gone
 
 
 def test_short_lookup_launches_stage_through_registers(sass):
