@@ -23,7 +23,8 @@ WANT = [
     ("launch__block_size", "block"),
     ("sm__cycles_elapsed.max", "cycles"),
 ]
-KEY = {"gma_aggregate_kernel": "gma_aggregate", "corr_lookup_kernel": "corr_lookup", "corr_gemm_pair_kernel": "corr_gemm",
+KEY = {"gma_aggregate_kernel": "gma_aggregate", "corr_lookup_ws_kernel": "corr_lookup", "corr_lookup_reg_kernel": "corr_lookup_1pair",
+       "pcblock_ffn1_kernel": "pcblock_ffn1", "corr_gemm_pair_kernel": "corr_gemm",
        "corr_gemm_kernel": "corr_gemm_1cta", "gma_stats_kernel": "gma_stats", "gma_cast_kernel": "gma_cast",
        "corr_pack_kernel": "corr_pack", "gma_proj_kernel": "gma_proj"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
