@@ -770,7 +770,15 @@ def run_ours(args):
             with torch.autocast("cuda", dtype=torch.float16):
                 return F.gelu(xin + ffn1(xin))
         ref_y = F.gelu(xin + ffn1(xin))
-        ffn_rel = _rel(sfb.pcblock_ffn1(xin, ffn1), ref_y)
+        torch.cuda.synchronize()
+        ours_y = sfb.pcblock_ffn1(xin, ffn1)
+        torch.cuda.synchronize()
+        ffn_rel = _rel(ours_y, ref_y)
+        # fp16 operands cannot reproduce the fp32 ops bit for bit: an exact 0.0 (seen once in ~10 runs, not reproduced by
+        # scripts/ffn1_stress.py) would mean the comparison did not see the kernel's output
+        if ffn_rel == 0.0 or ours_y.data_ptr() == ref_y.data_ptr():
+            raise SystemExit("bench.py: pcblock_ffn1 check compared a tensor with itself")
+        del ours_y
         us_ref_ffn = _time_events(ref_ffn, 20, 5, lambda: torch.cuda.synchronize()) * 1e3
         fl = 2.0 * PAIRS * N * 324 * 486 * 2
         kernels["pcblock_ffn1"] = {"us_per_launch": us_ffn, "reference_ops_us": us_ref_ffn, "speedup": us_ref_ffn / us_ffn,
