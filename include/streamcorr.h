@@ -9,6 +9,8 @@
  *   sf_corr_lookup[_group]  <- CorrBlock.__call__ + bilinear_sampler   core/corr.py:23-44, core/utils/utils.py:65-79
  *   sf_gma_attention        <- gma.Attention.forward                   core/gma.py:53-65
  *   sf_gma_aggregate        <- gma.Aggregate.forward                   core/gma.py:91-104
+ *   sf_upsample_flow        <- SKFlow_MF8.upsample_flow                core/models/streamflow.py:82-93   (8(f) row 3)
+ *   sf_pcblock_ffn1         <- first line of PCBlock4_Deep_nopool_res.forward    core/update.py:18-22, 31   (8(f) row 2)
  *
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; the library never
@@ -33,7 +35,7 @@ extern "C" {
 #define SF_API
 #endif
 
-#define SF_VERSION 200          /* major*100 + minor */
+#define SF_VERSION 210          /* major*100 + minor */
 #define SF_NUM_LEVELS 4         /* corr_levels fixed by the model: core/models/streamflow.py:38 */
 #define SF_RADIUS 4             /* corr_radius fixed by the model: core/models/streamflow.py:39 */
 #define SF_MAX_GROUPS 8         /* CorrBlocks batched into one lookup launch */

@@ -33,7 +33,7 @@ def test_exports_every_header_symbol(L):
 
 def test_version_and_level_geometry(L):
     from streamflow_b200 import _lib
-    assert L.sf_version() == 200
+    assert L.sf_version() == 210
     # Sintel 55x128 and BASELINE configs[0] 46x62 (floor-mode pooling, pitch rounded up to 4 floats)
     assert [_lib.level_dims(55, 128, l) for l in range(4)] == [(55, 128, 14, 32), (27, 64, 7, 16), (13, 32, 4, 8),
                                                                (6, 16, 2, 4)]
