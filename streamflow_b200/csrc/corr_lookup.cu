@@ -267,13 +267,26 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
         const unsigned win_u32 = static_cast<unsigned>(__cvta_generic_to_shared(win0));
         unsigned long long policy;
         asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-        auto stage_query = [&](int buf, int lq, const Pending& pd) {
-            const Origin og = window_origin(c, pd);
+        // The address arithmetic of an item (coordinates -> window origin -> tile address) is done BEFORE the loader waits
+        // for its buffer, so that only the cp.async issue itself sits between "buffer free" and "requests in flight".
+        struct Prep {
+            Origin og;
+            const float* src;
+        };
+        auto prep_query = [&](const Pending& pd) {
+            Prep r;
+            r.og = window_origin(c, pd);
+            const int tx0 = r.og.x0 >> 2, ty0 = r.og.y0 >> 2;
+            r.src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid < 0 ? 0 : pd.qid) * c.img + ((ty0 * c.tw + tx0) * 16 + rr * 4);
+            return r;
+        };
+        auto stage_query = [&](int buf, int lq, const Pending& pd, const Prep& pr) {
+            const Origin& og = pr.og;
             const int ox = og.x0 & 3, oy = og.y0 & 3;
             if (rr == 0) write_meta(p, c, pd, og, meta[buf], lq, lq == 0);
             if (pd.qid < 0) return;
             const int tx0 = og.x0 >> 2, ty0 = og.y0 >> 2;
-            const float* src = p.lvl[pd.grp][c.lvl] + static_cast<long long>(pd.qid) * c.img + ((ty0 * c.tw + tx0) * 16 + rr * 4);
+            const float* src = pr.src;
             const unsigned dst = win_u32 + static_cast<unsigned>((buf * (kQ * kStrideA) + lq * kStrideA + (rr - oy) * kPitchA) * 4);
             const bool c4 = (ox == 3);
             const unsigned utx = static_cast<unsigned>(tx0), utw = static_cast<unsigned>(c.tw);
@@ -302,9 +315,10 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
             c.advance();
             load_coords(p, c, lq0, pa);                     // coordinates of the next item: in flight during this one
             load_coords(p, c, lq0 + 16, pb);
+            const Prep ra = prep_query(qa), rb = prep_query(qb);
             mbar_wait_(&empty[buf], ((k >> 1) & 1) ^ 1);    // the compute warps are done with item k-2
-            stage_query(buf, lq0, qa);
-            stage_query(buf, lq0 + 16, qb);
+            stage_query(buf, lq0, qa, ra);
+            stage_query(buf, lq0 + 16, qb, rb);
             cp_async_mbar_arrive(&full[buf]);               // fires when this thread's chunks have landed
             mbar_arrive_(&full[buf]);                       // metadata written (release)
         }

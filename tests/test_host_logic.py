@@ -106,3 +106,57 @@ def test_single_process_paths():
     frames = [torch.full((3, 4, 4), float(i)) for i in range(9)]
     flows = sfd.run_windows(frames, lambda w: [torch.zeros(2, 4, 4) + float(w[k][0, 0, 0]) for k in range(3)], T=4)
     assert flows.shape == (8, 2, 4, 4) and [float(f[0, 0, 0]) for f in flows] == list(range(8))
+
+
+def test_next_row_entry_points_fail_loudly_without_a_device():
+    """pcblock_ffn1 / GraphedModel / patch_motion_encoder host logic: CPU tensors and unsupported widths raise StreamCorrError
+    before any kernel is touched (no CPU fallback), and the patch is reversible."""
+    import torch
+    import torch.nn as nn
+    import streamflow_b200 as sfb
+    from streamflow_b200 import pcblock
+
+    ffn1 = nn.Sequential(nn.Conv2d(32, 48, 1), nn.GELU(), nn.Conv2d(48, 32, 1)).eval()
+    with torch.no_grad():
+        with pytest.raises(sfb.StreamCorrError):
+            sfb.pcblock_ffn1(torch.randn(1, 32, 4, 4), ffn1)                 # not a CUDA tensor
+    # weight packing: zero padding to (ceil128(hidden), ceil64(C)) / (ceil16(C), ceil128(hidden)), cached per module
+    w1p, b1p, w2p, b2, C, Hd = pcblock._pack(ffn1)
+    assert (C, Hd) == (32, 48) and w1p.shape == (128, 64) and w2p.shape == (32, 128) and b1p.shape == (128,)
+    assert torch.equal(w1p[:48, :32].float(), ffn1[0].weight.detach().reshape(48, 32).half().float())
+    assert float(w1p[48:].abs().max()) == 0.0 and float(w1p[:, 32:].abs().max()) == 0.0 and float(b1p[48:].abs().max()) == 0.0
+    assert pcblock._pack(ffn1)[0] is w1p                                       # cache hit
+    with torch.no_grad():
+        ffn1[0].weight.mul_(2.0)
+    assert pcblock._pack(ffn1)[0] is not w1p                                   # in-place update -> repacked
+    with pytest.raises(sfb.StreamCorrError):
+        pcblock._pack(nn.Sequential(nn.Conv2d(640, 960, 1), nn.GELU(), nn.Conv2d(960, 640, 1)))    # gru width: unsupported
+    with pytest.raises(sfb.StreamCorrError):
+        pcblock._pack(nn.Sequential(nn.Conv2d(32, 48, 3, padding=1), nn.GELU(), nn.Conv2d(48, 32, 1)))
+
+    class Blk(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.ffn1 = nn.Sequential(nn.Conv2d(c, int(1.5 * c), 1), nn.GELU(), nn.Conv2d(int(1.5 * c), c, 1))
+            self.conv_list = nn.ModuleList()
+            self.pw = nn.Conv2d(c, c, 1)
+            self.ffn2 = nn.Identity()
+
+        def forward(self, x):
+            return "reference forward"
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.update_block = nn.Module()
+            self.update_block.encoder = nn.Module()
+            self.update_block.encoder.convc1 = Blk(324)
+            self.update_block.encoder.conv = Blk(640)                          # too wide: left alone
+
+    m = Model().eval()
+    assert sfb.patch_motion_encoder(m) == ["convc1"]
+    assert "forward" in m.update_block.encoder.convc1.__dict__ and "forward" not in m.update_block.encoder.conv.__dict__
+    sfb.unpatch_motion_encoder(m)
+    assert m.update_block.encoder.convc1(None) == "reference forward"
+    with pytest.raises(sfb.StreamCorrError):
+        sfb.GraphedModel(m, (4, 3, 64, 64))                                    # model not on a CUDA device
