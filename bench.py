@@ -28,7 +28,7 @@ JSON line (rank 0)
   torch_gpu_baseline   the reference's own torch ops for the hot path on the SAME B200 (TF32 off = its default, and on).
   full_model           whole-forward frames/s of the unmodified reference model on its own operators vs on the B200
                        operators (same GPU, same weights), hot-path share of each.
-  configs              KITTI- and Spring-shaped hot-path throughput (BASELINE.json configs[2], [3]), 1 GPU.
+  configs              KITTI- and Spring-shaped hot-path throughput (BASELINE.json configs[2], [3]), one clip per GPU.
   streaming, kitti_x8  BASELINE.json configs[4] and [2] across the N ranks with the NCCL flow gather inside the timed
                        region (64 frames -> 21 windows -> 63 flows; 8 KITTI clips sharded 8/N per GPU, strong scaling).
   cpu_baseline         the reference's own CorrBlock / Attention / Aggregate (oracle/_ref, `kind: "reference"`; the
@@ -732,9 +732,10 @@ def run_ours(args):
                                                   "us_per_extra_pair": (us_lk8 - us_lk1) / 7.0,
                                                   "frac_8_pairs": 2904 * 8 * N / us_lk8 / 1e3 / hbm,
                                                   "frac_marginal": 2904 * N / ((us_lk8 - us_lk1) / 7.0) / 1e3 / hbm,
-                                                  "note": "1 / 3 / 8 pairs per launch: the rate per extra pair does not improve "
-                                                          "with launch size, i.e. the gather itself (51 G 64-byte blocks/s), not a "
-                                                          "fixed per-launch cost, sets the fraction"}}
+                                                  "note": "1 / 3 / 8 pairs per launch (1 pair = the register-staged kernel, longer "
+                                                          "launches the warp-specialised cp.async kernel): the rate per extra pair "
+                                                          "does not improve with launch size, i.e. the gather behind the SM's staging "
+                                                          "buffers, not a fixed per-launch cost, sets the fraction"}}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D * PAIRS                     # one launch builds the pyramids of all pairs
         us_ev, us = us, us_graph["corr_gemm"]
@@ -814,19 +815,21 @@ def run_ours(args):
         del run
         torch.cuda.empty_cache()
 
-    # ---- KITTI- and Spring-shaped hot path (BASELINE.json configs[2], [3]), rank 0 at N=1
+    # ---- KITTI- and Spring-shaped hot path (BASELINE.json configs[2], [3]): one clip per rank (weak scaling like the
+    # headline), time = max over ranks, flows/s = all ranks' flows
     configs = None
-    if rank == 0 and world == 1 and not args.quick:
+    if not args.quick:
         configs = {}
         for name in ("kitti_376x1248", "spring_1080x1920"):
             h8, w8 = SHAPES[name][2:]
-            hi = make_inputs(7, h8, w8)
+            hi = make_inputs(7 + rank, h8, w8)
             res = {k: hi[k].to(dev) for k in ("fm_nhwc", "inps", "mfs", "coords")}
             gcall = sfb.GraphedCall(lambda: hot(res))
             reps = 20 if name.startswith("kitti") else 4
-            ms = _time_events(gcall, reps, 2, barrier)
+            ms = max_over_ranks(_time_events(gcall, reps, 2, barrier))
             n_ = h8 * w8
-            configs[name] = {"ms_per_clip": ms, "flows_per_s": PAIRS / (ms / 1e3), "N": n_, "steps": reps,
+            configs[name] = {"ms_per_clip": ms, "flows_per_s": world * PAIRS / (ms / 1e3), "N": n_, "steps": reps,
+                             "clips_per_gpu": 1,
                              "pyramid_gb": PAIRS * 4 * n_ * sum(((h8 >> l) + 3) // 4 * (((w8 >> l) + 3) // 4) * 16
                                                                for l in range(4)) / 1e9,
                              "softmax_numerators_gb": PAIRS * L.sf_gma_e_elems(1, n_) * 2 / 1e9,

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "sf_internal.h"
+#include "sm100_ptx.cuh"
 
 namespace sf {
 
@@ -213,29 +214,8 @@ constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof
 constexpr int kThreadsW = 192;
 
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar)))
-                 : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_init_(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_(uint64_t* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P;\n\t}\n"
-            : "=r"(ok)
-            : "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-
 template <bool kHalfOut>
 __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __grid_constant__ LookupParams p) {
     extern __shared__ __align__(16) float smem_f[];
@@ -251,10 +231,10 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
     c.init(p);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init_(&full[i], 128);      // per loader thread: one arrival of its cp.async group + one after its metadata
-            mbar_init_(&empty[i], 4);       // one per compute warp
+            mbar_init(&full[i], 128);      // per loader thread: one arrival of its cp.async group + one after its metadata
+            mbar_init(&empty[i], 4);       // one per compute warp
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     pdl_launch();
     __syncthreads();
@@ -316,11 +296,11 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
             load_coords(p, c, lq0, pa);                     // coordinates of the next item: in flight during this one
             load_coords(p, c, lq0 + 16, pb);
             const Prep ra = prep_query(qa), rb = prep_query(qb);
-            mbar_wait_(&empty[buf], ((k >> 1) & 1) ^ 1);    // the compute warps are done with item k-2
+            mbar_wait(&empty[buf], ((k >> 1) & 1) ^ 1);    // the compute warps are done with item k-2
             stage_query(buf, lq0, qa, ra);
             stage_query(buf, lq0 + 16, qb, rb);
             cp_async_mbar_arrive(&full[buf]);               // fires when this thread's chunks have landed
-            mbar_arrive_(&full[buf]);                       // metadata written (release)
+            mbar_arrive(&full[buf]);                       // metadata written (release)
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
@@ -328,10 +308,10 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
         int k = 0;
         for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
             const int buf = k & 1;
-            mbar_wait_(&full[buf], (k >> 1) & 1);
+            mbar_wait(&full[buf], (k >> 1) & 1);
             stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane, (warp + k) & 3);
             __syncwarp();
-            if (lane == 0) mbar_arrive_(&empty[buf]);
+            if (lane == 0) mbar_arrive(&empty[buf]);
         }
     }
 }
