@@ -24,7 +24,8 @@
 // its N (measured: 24 N = 64 MMAs took 1.5 us; the A tile read sets the floor), hence N = 128 for GEMM1 -- all the TMEM left
 // next to Y allows -- and only two MMAs per k-step for GEMM2.
 // TMEM: 128 columns of D1 + N2 <= 384 columns of Y.  The kernel is bound by the 128 x (Hp + N2) GELU evaluations per
-// tile on the FP32 pipe (erf by Abramowitz-Stegun 7.1.28, |err| < 3e-7, one MUFU.RCP), not by the tensor pipe.
+// tile on the FP32 pipe (erf by Abramowitz-Stegun 7.1.28, |err| < 3e-7, one MUFU.RCP; evaluated two at a time with the
+// packed FFMA2 / FMUL2 instructions of sm_100: 62.5 -> 52.1 us), not by the tensor pipe.
 #include <algorithm>
 
 #include "sf_internal.h"
@@ -82,6 +83,50 @@ __device__ __forceinline__ float gelu_erf(float v) {
     const float e = copysignf(1.0f - r, v);
     const float hv = 0.5f * v;
     return fmaf(hv, e, hv);
+}
+
+// Two GELUs at once on the packed-fp32 pipe (FFMA2 / FMUL2, sm_100): the same arithmetic as gelu_erf, 20 instructions per pair
+// instead of 32.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ void gelu_erf2(float v0, float v1, float& g0, float& g1) {
+    const unsigned long long a = mul2(pack2(fabsf(v0), fabsf(v1)), pack2(0.70710678118654752f, 0.70710678118654752f));
+    unsigned long long p = fma2(a, pack2(0.0000430638f, 0.0000430638f), pack2(0.0002765672f, 0.0002765672f));
+    p = fma2(a, p, pack2(0.0001520143f, 0.0001520143f));
+    p = fma2(a, p, pack2(0.0092705272f, 0.0092705272f));
+    p = fma2(a, p, pack2(0.0422820123f, 0.0422820123f));
+    p = fma2(a, p, pack2(0.0705230784f, 0.0705230784f));
+    p = fma2(a, p, pack2(1.0f, 1.0f));
+    p = mul2(p, p);
+    p = mul2(p, p);
+    p = mul2(p, p);
+    p = mul2(p, p);
+    float p0, p1, r0, r1;
+    unpack2(p, p0, p1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
+    const unsigned long long e = fma2(pack2(r0, r1), pack2(-1.0f, -1.0f), pack2(1.0f, 1.0f));
+    float e0, e1;
+    unpack2(e, e0, e1);
+    const unsigned long long hv = mul2(pack2(v0, v1), pack2(0.5f, 0.5f));
+    const unsigned long long g = fma2(hv, pack2(copysignf(e0, v0), copysignf(e1, v1)), hv);
+    unpack2(g, g0, g1);
 }
 
 __device__ __forceinline__ float to_float(float v) { return v; }
@@ -296,8 +341,8 @@ __global__ void __launch_bounds__(kThreadsFfn, 1) pcblock_ffn1_kernel(const __gr
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float2 bb = *reinterpret_cast<const float2*>(bs + 2 * j);
-                    const float g0 = gelu_erf(__uint_as_float(acc[half][2 * j]) + bb.x);
-                    const float g1 = gelu_erf(__uint_as_float(acc[half][2 * j + 1]) + bb.y);
+                    float g0, g1;
+                    gelu_erf2(__uint_as_float(acc[half][2 * j]) + bb.x, __uint_as_float(acc[half][2 * j + 1]) + bb.y, g0, g1);
                     __half2 t = __floats2half2_rn(g0, g1);
                     pk[j] = *reinterpret_cast<uint32_t*>(&t);
                 }
@@ -344,9 +389,12 @@ __global__ void __launch_bounds__(kThreadsFfn, 1) pcblock_ffn1_kernel(const __gr
             const int c0 = cb * 16;
             OT* dst = og + static_cast<size_t>(c0) * cstride;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float y = gelu_erf(__uint_as_float(acc[j]) + b2s[c0 + j] + xcur[j]);
-                if (live && c0 + j < a.C) st_stream(dst + j * cstride, y);
+            for (int j = 0; j < 16; j += 2) {
+                float y0, y1;
+                gelu_erf2(__uint_as_float(acc[j]) + b2s[c0 + j] + xcur[j], __uint_as_float(acc[j + 1]) + b2s[c0 + j + 1] + xcur[j + 1],
+                          y0, y1);
+                if (live && c0 + j < a.C) st_stream(dst + j * cstride, y0);
+                if (live && c0 + j + 1 < a.C) st_stream(dst + (j + 1) * cstride, y1);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) xcur[j] = xnext[j];

@@ -77,9 +77,10 @@ def test_short_lookup_launches_stage_through_registers(sass):
 
 def test_motion_encoder_entry_is_a_two_gemm_tcgen05_kernel(sass):
     """sf_pcblock_ffn1: both 1x1 convolutions on tcgen05 (4 + 4 MMA issue sites), weights by TMA, accumulators read back with
-    tcgen05.ld, GELU via one MUFU.RCP, no issue waterfall, no spills."""
+    tcgen05.ld, GELU pairs via FFMA2 / FMUL2 and one MUFU.RCP each, no issue waterfall, no spills."""
     k = kernel(sass, "19pcblock_ffn1_kernelIffE")
     assert count(k, "UTCHMMA") >= 8 and count(k, "UTMALDG") >= 3 and count(k, "LDTM") >= 3 and count(k, "MUFU.RCP") >= 16
+    assert count(k, "FFMA2") >= 64 and count(k, "FMUL2") >= 48            # GELU pairs on the packed-fp32 pipe
     assert count(k, "BRA.U.ANY") == 0 and count(k, "STL") == 0 and count(k, "LDL") == 0
 
 
