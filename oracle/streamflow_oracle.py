@@ -186,6 +186,30 @@ def aggregate(attn: np.ndarray, fmap: np.ndarray, w_v: np.ndarray, gamma: float,
     return (x + dtype(gamma) * out).astype(dtype, copy=False)
 
 
+# ----------------------------------------------------------------- motion-encoder entry
+def _erf(x: np.ndarray) -> np.ndarray:
+    """erf by its Maclaurin / continued-fraction free closed form is not in NumPy: use math.erf element-wise (exact to double
+    rounding; the fixtures are small)."""
+    import math
+    return np.vectorize(math.erf, otypes=[np.float64])(x)
+
+
+def gelu(x: np.ndarray) -> np.ndarray:
+    """torch.nn.GELU() / F.gelu default (approximate='none'): 0.5 x (1 + erf(x / sqrt 2))."""
+    x = np.asarray(x, dtype=np.float64)
+    return 0.5 * x * (1.0 + _erf(x / np.sqrt(2.0)))
+
+
+def pcblock_ffn1(x: np.ndarray, w1: np.ndarray, b1: np.ndarray, w2: np.ndarray, b2: np.ndarray) -> np.ndarray:
+    """First line of PCBlock4_Deep_nopool_res.forward, core/update.py:31, with ffn1 = Conv2d(C, 1.5 C, 1) -> GELU ->
+    Conv2d(1.5 C, C, 1) (core/update.py:18-22):  gelu(x + W2 . gelu(W1 . x + b1) + b2)  per pixel.  x: [P, C, h, w];
+    w1: [H, C], w2: [C, H].  float64 throughout."""
+    x = np.asarray(x, dtype=np.float64)
+    hid = gelu(np.einsum("oc,pchw->pohw", np.asarray(w1, np.float64), x) + np.asarray(b1, np.float64)[None, :, None, None])
+    y = np.einsum("oc,pchw->pohw", np.asarray(w2, np.float64), hid) + np.asarray(b2, np.float64)[None, :, None, None]
+    return gelu(x + y)
+
+
 # ----------------------------------------------------------------- whole hot path
 def hot_path(fmaps, coords_per_iter, inps, mfs, w_qk, w_v, gamma, dtype=np.float32):
     """One clip through the hot path, the shape ``bench.py`` times.

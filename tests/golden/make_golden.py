@@ -152,8 +152,28 @@ def case_upsample():
     np.savez_compressed(os.path.join(OUT, "upsample.npz"), flow=flow, mask=mask, out=up.numpy())
 
 
+def case_pcblock():
+    """The reference's own PCBlock4_Deep_nopool_res (core/update.py:12-36, imported through the timm shim like the model):
+    inputs, ffn1 parameters, and the value of the first line of its forward, `F.gelu(x + self.ffn1(x))` (core/update.py:31),
+    in fp32 on the CPU."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import ref_model as rm
+    mod = rm.load_model_module("reference")
+    upd = mod._l1_modules["update"]
+    torch.manual_seed(50)
+    blk = upd.PCBlock4_Deep_nopool_res(48, 32, [1, 15]).eval()
+    x = torch.from_numpy(rs_normal(51, (2, 48, 5, 7)) * np.float32(1.5))
+    with torch.no_grad():
+        first = torch.nn.functional.gelu(x + blk.ffn1(x))
+        full = blk(x)
+    np.savez_compressed(os.path.join(OUT, "pcblock.npz"), x=x.numpy(), w1=blk.ffn1[0].weight.detach().numpy().reshape(72, 48),
+                        b1=blk.ffn1[0].bias.detach().numpy(), w2=blk.ffn1[2].weight.detach().numpy().reshape(48, 72),
+                        b2=blk.ffn1[2].bias.detach().numpy(), first=first.numpy(), block_out=full.numpy())
+
+
 if __name__ == "__main__":
     case_upsample()
+    case_pcblock()
     case_corr_small()
     case_corr_batch()
     case_corr_cfg1()

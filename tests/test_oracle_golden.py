@@ -131,3 +131,15 @@ def test_pooling_is_linear():
     f2p = so.avg_pool2x2(f2)
     vol1 = np.matmul(f1.reshape(1, 24, -1).transpose(0, 2, 1), f2p.reshape(1, 24, -1)) / np.sqrt(np.float32(24))
     assert rel_err(vol1.reshape(pyr[1].shape), pyr[1]) < TOL
+
+
+def test_pcblock_entry_numpy():
+    """oracle.pcblock_ffn1 against the value of `F.gelu(x + self.ffn1(x))` (core/update.py:31) computed by
+    the reference's own PCBlock4_Deep_nopool_res (tests/golden/make_golden.py::case_pcblock)."""
+    g = load_golden("pcblock.npz")
+    out = so.pcblock_ffn1(g["x"], g["w1"], g["b1"], g["w2"], g["b2"])
+    assert out.shape == g["first"].shape
+    assert rel_err(out, g["first"]) < 2e-6          # the reference ran in fp32, the oracle in fp64
+    # GELU restatement alone against torch's
+    x = np.linspace(-6, 6, 97)
+    assert np.allclose(so.gelu(x), torch.nn.functional.gelu(torch.from_numpy(x)).numpy(), atol=1e-12)

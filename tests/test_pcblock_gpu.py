@@ -47,6 +47,22 @@ def test_ffn1_against_torch_fp32(C, P, h, w, dtype):
     assert e < 2.0 * _rel(amp.float(), ref) + 2e-4
 
 
+def test_ffn1_against_the_reference_fixture():
+    """tests/golden/pcblock.npz: inputs, parameters and `F.gelu(x + self.ffn1(x))` of the reference's own
+    PCBlock4_Deep_nopool_res (fp32, CPU), plus the NumPy oracle on the same data."""
+    import streamflow_b200 as sfb
+    from oracle import streamflow_oracle as so
+    from tests.helpers import load_golden, rel_err
+    g = load_golden("pcblock.npz")
+    C, H = g["w2"].shape
+    ffn1 = nn.Sequential(nn.Conv2d(C, H, 1), nn.GELU(), nn.Conv2d(H, C, 1)).cuda().eval()
+    with torch.no_grad():
+        ffn1[0].weight.copy_(torch.from_numpy(g["w1"]).view(H, C, 1, 1)); ffn1[0].bias.copy_(torch.from_numpy(g["b1"]))
+        ffn1[2].weight.copy_(torch.from_numpy(g["w2"]).view(C, H, 1, 1)); ffn1[2].bias.copy_(torch.from_numpy(g["b2"]))
+        out = sfb.pcblock_ffn1(torch.from_numpy(g["x"]).cuda(), ffn1).cpu().numpy()
+    assert rel_err(out, g["first"]) < 2e-3 and rel_err(out, so.pcblock_ffn1(g["x"], g["w1"], g["b1"], g["w2"], g["b2"])) < 2e-3
+
+
 def test_ffn1_weight_update_and_errors():
     import streamflow_b200 as sfb
     ffn1 = _ffn1(128, seed=1)
