@@ -35,7 +35,7 @@ constexpr int kThreads = 128;       // 4 warps: a loader quad per query, 4 row g
                                     // 8 row groups were measured: 18.7 us against 16.8 us, the extra row loads of stage C cost more)
 
 // Per-item metadata for stage C, written by one lane of each loader quad.
-struct Meta {
+struct alignas(16) Meta {
     float ax[kQ], ay[kQ];
     int o[kQ];                   // x0 & 3: window origin inside its first tile column; -1: query out of range
     unsigned out_off[kQ];        // element offset of out[b, lvl*81, n] inside the group's output tensor
@@ -207,22 +207,29 @@ __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const float* src,
 constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof(Meta));
 
 // ===================================================================================================================
-// Kernel 1 (long launches, warp-specialised cp.async): stage A/B runs in two LOADER warps and stage C in four COMPUTE warps, coupled by mbarriers (full[buf]: the loaders' cp.async groups + metadata have landed;
-// empty[buf]: the compute warps are done with the buffer) instead of two block-wide barriers per item.  A loader thread
-// owns row rr of the tiles of TWO queries (lq and lq + 16).  The compute warps never execute loader instructions, and the
-// loaders run up to two items ahead.
-constexpr int kThreadsW = 192;
+// Kernel 1 (default, warp-specialised cp.async): stage A/B runs in four LOADER warps (a lane quad per query) and stage C in four
+// COMPUTE warps, coupled by mbarriers (full[buf]: the loaders' cp.async groups + metadata have landed; empty[buf]: the compute
+// warps are done with the buffer) instead of block-wide barriers.  The compute warps never execute loader instructions; the
+// loaders run up to three items ahead (3 buffers per CTA, 3 CTAs per SM) and do the address arithmetic of their next item
+// before they wait for its buffer.  Measured configurations (3 pairs / 1 pair, us): 2 buffers x 5 CTAs with 2 loader warps
+// 15.85 / 7.36; 3 x 3 with 2 loader warps 15.86 / 6.71; 3 x 3 with 4 loader warps 15.39 / 6.36 (kept); 5 x 2 with 4 loader warps
+// and two compute groups 15.34 / 6.54.
+constexpr int kLoaderWarpsW = 4;      // 4: one query per loader quad; 2: a loader thread owns two queries (lq, lq + 16)
+constexpr int kGroupsW = 1;           // interpolation groups of 4 warps; group g takes the items k = g (mod kGroupsW)
+constexpr int kThreadsW = 128 * kGroupsW + 32 * kLoaderWarpsW;
+constexpr int kBufsW = 3;            // staging buffers per CTA
+constexpr int kCtasW = 3;            // resident CTAs per SM
 
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 template <bool kHalfOut>
-__global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __grid_constant__ LookupParams p) {
+__global__ void __launch_bounds__(kThreadsW, kCtasW) corr_lookup_ws_kernel(const __grid_constant__ LookupParams p) {
     extern __shared__ __align__(16) float smem_f[];
-    float* win0 = smem_f;                                   // [2][kQ * kStrideA]
-    Meta* meta = reinterpret_cast<Meta*>(smem_f + 2 * kQ * kStrideA);   // [2]
-    uint64_t* full = reinterpret_cast<uint64_t*>(meta + 2);  // [2]
-    uint64_t* empty = full + 2;                              // [2]
+    float* win0 = smem_f;                                   // [kBufsW][kQ * kStrideA]
+    Meta* meta = reinterpret_cast<Meta*>(smem_f + kBufsW * kQ * kStrideA);   // [kBufsW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(meta + kBufsW);  // [kBufsW]
+    uint64_t* empty = full + kBufsW;                              // [kBufsW]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -230,8 +237,8 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
     Cta c;
     c.init(p);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&full[i], 128);      // per loader thread: one arrival of its cp.async group + one after its metadata
+        for (int i = 0; i < kBufsW; ++i) {
+            mbar_init(&full[i], 64 * kLoaderWarpsW);      // per loader thread: one arrival of its cp.async group + one after its metadata
             mbar_init(&empty[i], 4);       // one per compute warp
         }
         fence_mbar_init();
@@ -240,9 +247,9 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
     __syncthreads();
     pdl_wait();
 
-    if (warp >= 4) {
+    if (warp >= 4 * kGroupsW) {
         // ------------------------------------------------------------------ loaders
-        const int lt = tid - 128;
+        const int lt = tid - 128 * kGroupsW;
         const int lq0 = lt >> 2, rr = lt & 3;
         const unsigned win_u32 = static_cast<unsigned>(__cvta_generic_to_shared(win0));
         unsigned long long policy;
@@ -285,41 +292,46 @@ __global__ void __launch_bounds__(kThreadsW, 5) corr_lookup_ws_kernel(const __gr
                 if (c4) cp_async16_zfill(d + (48u ^ x), s + 48, rbad || !cok3, policy);
             }
         };
+        constexpr bool kTwo = kLoaderWarpsW == 2;
         Pending pa, pb;
         load_coords(p, c, lq0, pa);
-        load_coords(p, c, lq0 + 16, pb);
+        if (kTwo) load_coords(p, c, lq0 + 16, pb);
         int k = 0;
         for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
-            const int buf = k & 1;
+            const int buf = k % kBufsW;
             const Pending qa = pa, qb = pb;
             c.advance();
             load_coords(p, c, lq0, pa);                     // coordinates of the next item: in flight during this one
-            load_coords(p, c, lq0 + 16, pb);
-            const Prep ra = prep_query(qa), rb = prep_query(qb);
-            mbar_wait(&empty[buf], ((k >> 1) & 1) ^ 1);    // the compute warps are done with item k-2
+            if (kTwo) load_coords(p, c, lq0 + 16, pb);
+            const Prep ra = prep_query(qa);
+            Prep rb;
+            if (kTwo) rb = prep_query(qb);
+            mbar_wait(&empty[buf], ((k / kBufsW) & 1) ^ 1);    // the compute warps are done with item k - kBufsW
             stage_query(buf, lq0, qa, ra);
-            stage_query(buf, lq0 + 16, qb, rb);
+            if (kTwo) stage_query(buf, lq0 + 16, qb, rb);
             cp_async_mbar_arrive(&full[buf]);               // fires when this thread's chunks have landed
             mbar_arrive(&full[buf]);                       // metadata written (release)
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ------------------------------------------------------------------ compute: lane = query
-        int k = 0;
-        for (int t = blockIdx.x >> 2; t < c.t_total; t += c.tstep, ++k) {
-            const int buf = k & 1;
-            mbar_wait(&full[buf], (k >> 1) & 1);
-            stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane, (warp + k) & 3);
+        const int grp = warp >> 2;
+        int k = grp;
+        for (int t = (blockIdx.x >> 2) + grp * c.tstep; t < c.t_total; t += kGroupsW * c.tstep, k += kGroupsW) {
+            const int buf = k % kBufsW;
+            mbar_wait(&full[buf], (k / kBufsW) & 1);
+            stage_c<kHalfOut, kPitchA, kSwzA>(p, meta[buf], win0 + buf * (kQ * kStrideA) + lane * kStrideA, lane,
+                                              (warp + k / kGroupsW) & 3);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[buf]);
         }
     }
 }
 
-constexpr int kLookupSmemW = kLookupSmemA + 64;
+constexpr int kLookupSmemW = kBufsW * kQ * kStrideA * 4 + kBufsW * static_cast<int>(sizeof(Meta)) + 64;
 
 // ===================================================================================================================
-// Kernel 2 (short launches, register-staged): the window chunks of item k+1 travel global -> REGISTERS (LDG.128, in flight during stage
+// Kernel 2 (cross-check, register-staged, STREAMCORR_LOOKUP=reg): the window chunks of item k+1 travel global -> REGISTERS (LDG.128, in flight during stage
 // C of item k) -> shared (STS.128, 4 wavefronts per warp instruction instead of one per returned sector), ONE window
 // buffer per CTA.  A loader lane (query, row rr inside a tile) owns at most 3 tile rows x 4 tile columns = 12 chunks.
 // Row pitch 24 floats (96 B) and query stride 244 floats (976 B): the loader's quarter-warp (2 queries x 4 rows) and
@@ -429,16 +441,17 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
                    p.tiles * groups * SF_NUM_LEVELS < (1ll << 31),
                "corr_lookup: %lld queries per group exceed the 32-bit index range of the kernel", p.BN);
     p.items = p.tiles * groups * SF_NUM_LEVELS;
-    // Short launches (fewer than two items per resident CTA: one Sintel / KITTI pair, the reference model's own per-pair
-    // calls) are dominated by latency and run the register-staged kernel (6.8 us vs 7.4 us for one Sintel pair), longer ones
-    // the warp-specialised cp.async kernel (16.0 us vs 17.3 us for three pairs).  STREAMCORR_LOOKUP = reg | ws forces one.
+    // One kernel for every launch size: the warp-specialised cp.async kernel (3 staging buffers x 3 CTAs per SM: 15.4 us for the
+    // three Sintel pairs, 6.4 us for one pair).  The register-staged kernel (17.3 / 6.9 us) is kept as an independently
+    // synchronised implementation of the same arithmetic (plain __syncthreads, clean under racecheck): the parity tests run both and
+    // require bit-identical results.  STREAMCORR_LOOKUP = reg | ws forces one.
     const int forced = [] {                                  // read per launch: the parity tests switch kernels
         const char* e = getenv("STREAMCORR_LOOKUP");
         if (e && e[0] == 'r') return 1;
         if (e && e[0] == 'w') return 0;
         return -1;
     }();
-    const int variant = forced >= 0 ? forced : (p.items < 2ll * 5 * num_sms ? 1 : 0);
+    const int variant = forced >= 0 ? forced : 0;
     auto launch = [&](auto kernel, int threads, int smem, int ctas_per_sm) -> int {
         // persistent CTAs; a multiple of 4: CTA c works on level c & 3 only (items is a multiple of 4)
         const int grid = static_cast<int>(std::min<long long>(p.items, static_cast<long long>(ctas_per_sm) * num_sms)) & ~3;
@@ -452,8 +465,8 @@ int launch_corr_lookup(const LookupParams& p_in, int groups, int num_sms, cudaSt
     if (variant == 1)
         return p.out_f16 ? launch(corr_lookup_reg_kernel<true>, kThreads, kLookupSmemB, kCtasB)
                          : launch(corr_lookup_reg_kernel<false>, kThreads, kLookupSmemB, kCtasB);
-    return p.out_f16 ? launch(corr_lookup_ws_kernel<true>, kThreadsW, kLookupSmemW, 5)
-                     : launch(corr_lookup_ws_kernel<false>, kThreadsW, kLookupSmemW, 5);
+    return p.out_f16 ? launch(corr_lookup_ws_kernel<true>, kThreadsW, kLookupSmemW, kCtasW)
+                     : launch(corr_lookup_ws_kernel<false>, kThreadsW, kLookupSmemW, kCtasW);
 }
 
 }  // namespace sf

@@ -67,9 +67,9 @@ def test_lookup_is_a_warp_specialised_cp_async_gather(sass):
     assert not any("18corr_lookup_kernel" in name for name in sass)      # the two-barrier kernel is gone
 
 
-def test_short_lookup_launches_stage_through_registers(sass):
-    """The latency-bound variant (one pair per launch): LDG.128 into registers, STS.128 into ONE window buffer, no
-    cp.async at all, no spills."""
+def test_cross_check_lookup_stages_through_registers(sass):
+    """The independently synchronised lookup kernel the parity tests compare the default one with bit for bit: LDG.128 into
+    registers, STS.128 into ONE window buffer, plain block barriers, no cp.async at all, no spills."""
     k = kernel(sass, "22corr_lookup_reg_kernelILb0E")
     assert count(k, "LDG.E.NA.128") >= 12 and count(k, "STS.128") >= 9 and count(k, "LDGSTS") == 0
     assert count(k, "STL") == 0 and count(k, "LDL") == 0
