@@ -732,10 +732,10 @@ def run_ours(args):
                                                   "us_per_extra_pair": (us_lk8 - us_lk1) / 7.0,
                                                   "frac_8_pairs": 2904 * 8 * N / us_lk8 / 1e3 / hbm,
                                                   "frac_marginal": 2904 * N / ((us_lk8 - us_lk1) / 7.0) / 1e3 / hbm,
-                                                  "note": "1 / 3 / 8 pairs per launch (1 pair = the register-staged kernel, longer "
-                                                          "launches the warp-specialised cp.async kernel): the rate per extra pair "
-                                                          "does not improve with launch size, i.e. the gather behind the SM's staging "
-                                                          "buffers, not a fixed per-launch cost, sets the fraction"}}
+                                                  "note": "1 / 3 / 8 pairs per launch, the same warp-specialised cp.async kernel: the rate "
+                                                          "per extra pair does not improve with launch size (it drops once the 2.1 GB of "
+                                                          "8 pyramids leave nothing of the previous launch in L2), i.e. the gather, not a "
+                                                          "fixed per-launch cost, sets the fraction"}}
         us, n = kernel_time(_lib.KERNEL_CORR_GEMM)
         flops = 2.0 * N * N * D * PAIRS                     # one launch builds the pyramids of all pairs
         us_ev, us = us, us_graph["corr_gemm"]

@@ -16,8 +16,8 @@
 //      (zeros outside the image); the lane quad fetches the four rows of ONE 64-byte tile, only the 10 window rows are staged;
 //   C  lane = query: conflict-free LDS.128 of its own rows, horizontal then vertical lerp in registers, one 128-byte
 //      coalesced store per output channel straight into the NCHW result (channel = l*81 + i*9 + j, i moves x, j moves y).
-// Two kernels share these stages: a warp-specialised cp.async kernel for long launches and a register-staged one for short
-// launches (see launch_corr_lookup).
+// Two kernels share these stages: the warp-specialised cp.async kernel every launch uses, and a register-staged one kept as an
+// independently synchronised cross-check (see launch_corr_lookup).
 #include <algorithm>
 #include <cstdlib>
 
