@@ -180,10 +180,11 @@ __device__ __forceinline__ void stage_c(const LookupParams& p, const Meta& m, co
 }
 
 // ===================================================================================================================
-// Staging layout of the cp.async kernel: per query 10 window rows of 16 floats (4 tile columns), two buffers of 32 queries.
+// Staging layout of the cp.async kernel: per query 10 window rows of 16 floats (4 tile columns), buffers of 32 queries.
 // History (profiles/r2_probes.txt): with loaders and interpolation in the SAME threads and two block-wide barriers per item
 // the gather (8.6 us alone) and stage C (6.2 us alone) did not overlap at all (17.1 us); leaner loader code, a rotated heavy
-// row share and the bank swizzle below brought that kernel to 16.4 us, warp specialisation (next) to 16.0 us.
+// row share and the bank swizzle below brought that kernel to 16.4 us, warp specialisation (next) to 16.0 us, deeper per-CTA
+// buffering with four loader warps to 15.4 us.
 constexpr int kPitchA = 16;                              // 4 tile columns of 4 floats per staged row
 constexpr int kStrideA = kRows * kPitchA + 4;            // 164 floats: 8 consecutive queries -> distinct bank quads
 constexpr bool kSwzA = true;                             // 16-byte chunk j of staged row wr lives at chunk j ^ ((wr >> 1) & 3): the four
@@ -203,8 +204,6 @@ __device__ __forceinline__ void cp_async16_zfill(unsigned dst, const float* src,
             ::"r"(dst), "l"(src), "r"(static_cast<int>(ignore)), "l"(policy)
             : "memory");
 }
-
-constexpr int kLookupSmemA = 2 * kQ * kStrideA * 4 + 2 * static_cast<int>(sizeof(Meta));
 
 // ===================================================================================================================
 // Kernel 1 (default, warp-specialised cp.async): stage A/B runs in four LOADER warps (a lane quad per query) and stage C in four
