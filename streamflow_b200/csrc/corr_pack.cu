@@ -60,30 +60,32 @@ __global__ void absmax2_kernel(Strided4 t0, Strided4 t1, int D, int h, int w, lo
     }
 }
 
-// dense per-batch blocks (NCHW-contiguous or channels-last): plain vectorised sweep of the storage
-__global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long sb0, long long sb1, int B,
-                                    long long per_batch, unsigned* out_bits) {
+// dense per-batch blocks (NCHW-contiguous or channels-last): plain vectorised sweep of the storage.  grid = (blocks, 2 operands,
+// B batches): every thread issues ALL its 16-byte loads before it reduces (the first version walked the batches one after the other
+// with four loads in flight: 14 us for the 29 MB of a Sintel clip), one atomic pair per CTA.
+__global__ void __launch_bounds__(256) absmax2_flat_kernel(const float* f0, const float* f1, long long sb0, long long sb1, int B,
+                                                           long long per_batch, unsigned* out_bits) {
+    __shared__ float s_m[8];
+    __shared__ unsigned s_low[8];
     pdl_launch();
     pdl_wait();
     const float* f = blockIdx.y == 0 ? f0 : f1;
     const long long sb = blockIdx.y == 0 ? sb0 : sb1;
     const long long n4 = per_batch >> 2;
+    const float4* v = reinterpret_cast<const float4*>(f + static_cast<long long>(blockIdx.z) * sb);
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     float m = 0.f;
     unsigned low = 0u;
-    for (int b = 0; b < B; ++b) {
-        const float4* v = reinterpret_cast<const float4*>(f + b * sb);
-        const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-        for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += 4 * stride) {
-            float4 q[4];
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += 8 * stride) {
+        float4 q[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)     // four independent 16-byte loads in flight per thread
-                q[u] = (i + u * stride < n4) ? __ldg(v + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < 8; ++u)         // eight independent 16-byte loads in flight per thread
+            q[u] = (i + u * stride < n4) ? __ldg(v + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                m = fmaxf(fmaxf(m, fmaxf(fabsf(q[u].x), fabsf(q[u].y))), fmaxf(fabsf(q[u].z), fabsf(q[u].w)));
-                low |= (__float_as_uint(q[u].x) | __float_as_uint(q[u].y) | __float_as_uint(q[u].z) |
-                        __float_as_uint(q[u].w)) & 0x1FFFu;
-            }
+        for (int u = 0; u < 8; ++u) {
+            m = fmaxf(fmaxf(m, fmaxf(fabsf(q[u].x), fabsf(q[u].y))), fmaxf(fabsf(q[u].z), fabsf(q[u].w)));
+            low |= (__float_as_uint(q[u].x) | __float_as_uint(q[u].y) | __float_as_uint(q[u].z) |
+                    __float_as_uint(q[u].w)) & 0x1FFFu;
         }
     }
 #pragma unroll
@@ -92,6 +94,16 @@ __global__ void absmax2_flat_kernel(const float* f0, const float* f1, long long 
         low |= __shfl_xor_sync(0xffffffffu, low, s);
     }
     if ((threadIdx.x & 31) == 0) {
+        s_m[threadIdx.x >> 5] = m;
+        s_low[threadIdx.x >> 5] = low;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            m = fmaxf(m, s_m[w]);
+            low |= s_low[w];
+        }
         if (m > 0.f) atomicMax(out_bits + blockIdx.y, __float_as_uint(m));
         if (low) atomicOr(out_bits + 2, low);
     }
@@ -231,9 +243,11 @@ int launch_absmax2(const float* f1, const float* f2, int64_t B, int64_t D, int64
     };
     if (dense(s1) && dense(s2) && per_batch % 4 == 0 && s1[0] % 4 == 0 && s2[0] % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0) {
-        const int fb = static_cast<int>(std::min<long long>((per_batch / 4 + 255) / 256, 592));
+        // one float4 x 8 per thread where the tensor is large enough; B <= 65535 batches ride in grid.z
+        const int fb = static_cast<int>(std::max<long long>(1, std::min<long long>((per_batch / 4 + 2047) / 2048, 592)));
+        SF_REQUIRE(B <= 65535, "corr_build: batch %lld too large", (long long)B);
         prof_before(SF_KERNEL_CORR_PACK, s);
-        SF_CUDA_CHECK(launch_kernel(absmax2_flat_kernel, dim3(fb, 2), dim3(256), 0, s, f1, f2, (long long)s1[0],
+        SF_CUDA_CHECK(launch_kernel(absmax2_flat_kernel, dim3(fb, 2, static_cast<unsigned>(B)), dim3(256), 0, s, f1, f2, (long long)s1[0],
                                     (long long)s2[0], static_cast<int>(B), per_batch, amax_bits));
         prof_after(SF_KERNEL_CORR_PACK, s);
         SF_CUDA_CHECK(cudaGetLastError());
