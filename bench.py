@@ -16,8 +16,10 @@ JSON line (rank 0)
              public-API calls of one clip captured once in a CUDA graph (streamflow_b200.GraphedCall) and replayed;
              `eager_ms_per_step` is the same calls issued eagerly (--eager makes that the headline).
   e2e        frames in -> flows out: the UNMODIFIED reference model (oracle/_ref: SKFlow_MF8 + SKUpdateBlock_TAM_v3 +
-             Twins_CSC) running on the B200 operators through streamflow_b200.install(); every step uploads the 4
-             uint8 frames from pinned host memory and downloads the 3 full-resolution flows.  Falls back to the
+             Twins_CSC) running on the B200 operators through streamflow_b200.install(), its whole forward replayed as one
+             CUDA graph per clip (streamflow_b200.GraphedModel; `e2e.eager_ms_per_step` = the same forward launched
+             eagerly, the two are checked against each other); every step uploads the 4 uint8 frames from pinned host
+             memory and downloads the 3 full-resolution flows.  Falls back to the
              hot-path call chain with host buffers when the reference snapshot is absent (`e2e.workload` says which).
   parity     the LAST timed step's lookup features and GMA result compared with the reference op sequence
              (oracle/torch_port, fp32, TF32 off) on the same GPU; the run fails above 1e-3.
@@ -27,7 +29,9 @@ JSON line (rank 0)
              `traffic` = dram bytes per launch read from the committed ncu summary (profiles/ncu_dram_bytes.json).
   torch_gpu_baseline   the reference's own torch ops for the hot path on the SAME B200 (TF32 off = its default, and on).
   full_model           whole-forward frames/s of the unmodified reference model on its own operators vs on the B200
-                       operators (same GPU, same weights), hot-path share of each.
+                       operators (same GPU, same weights), hot-path share of each; `all_patches` = plus the two optional
+                       caller-side patches (patch_upsample, patch_motion_encoder = sf_pcblock_ffn1).
+  kernels.pcblock_ffn1 SURVEY 8(f) row 2: the motion encoder's entry on the lookup output, against the reference's eager ops.
   configs              KITTI- and Spring-shaped hot-path throughput (BASELINE.json configs[2], [3]), one clip per GPU.
   streaming, kitti_x8  BASELINE.json configs[4] and [2] across the N ranks with the NCCL flow gather inside the timed
                        region (64 frames -> 21 windows -> 63 flows; 8 KITTI clips sharded 8/N per GPU, strong scaling).
