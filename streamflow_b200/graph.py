@@ -62,6 +62,9 @@ class GraphedModel:
 
     ``frames`` are copied into the graph's static input; the returned tensor is the graph's static output (overwritten
     by the next call).  Padding to a multiple of 8 follows the reference's ``InputPadder`` ('sintel' or 'kitti' mode).
+    The graph is tied to the model's parameter STORAGE: in-place weight updates are picked up by the reference's own
+    modules, but re-create the ``GraphedModel`` after ``load_state_dict`` into new tensors, after moving the model, or after
+    ``patch_motion_encoder`` / ``patch_upsample`` (the packed fp16 weights of ``sf_pcblock_ffn1`` are made at capture time).
     """
 
     def __init__(self, model, frames_shape, iters: int = 12, pad_mode: str = "sintel", warmup: int = 2):
